@@ -1,0 +1,170 @@
+/*
+ * ultrasphere_b200 — C ABI of the B200 (sm_100a) hot path.
+ *
+ * The reference (ultrasphere 2.0.4) is pure Python and has no FFI of its own; its only seams
+ * for this path are the Python methods below.  Each entry point here is what a binding for
+ * that method calls once the host side has flattened the dict-of-arrays into pointer tables
+ * (INTEGRATION.md shows the ctypes stub a maintainer would add):
+ *
+ *   us_to_cartesian      replaces the array work of SphericalCoordinates.to_cartesian
+ *                        (src/ultrasphere/_coordinates.py:636-656)
+ *   us_from_cartesian    replaces the array work of SphericalCoordinates.from_cartesian
+ *                        (src/ultrasphere/_coordinates.py:555-579)
+ *   us_weighted_reduce   replaces the axis-by-axis vecdot contraction of integrate()'s dense
+ *                        branch (src/ultrasphere/_integral.py:261-276)
+ *   us_separable_reduce  replaces the per-axis vecdot of integrate()'s separable branch
+ *                        (src/ultrasphere/_integral.py:245-260)
+ *   us_plan_compile      replaces the per-call graph walk (nx.topological_sort + get_child,
+ *                        _coordinates.py:566-574, 638-644) by a one-off flattening of the
+ *                        branching-type expression (_coordinates.py:206-242) into a program
+ *
+ * Conventions
+ *   - plain C types only; every pointer named *_dev is a CUDA device pointer owned by the
+ *     caller; the library never allocates, frees or retains caller-visible memory
+ *   - all launches are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the
+ *     legacy default stream); no entry point synchronises
+ *   - return value: 0 on success, >0 a cudaError_t, <0 one of US_E*; the message is available
+ *     from us_last_error_string() (thread-local).  Nothing throws across the boundary.
+ *   - there is no CPU fallback: without a usable CUDA device the calls return an error.
+ */
+#ifndef ULTRASPHERE_B200_H
+#define ULTRASPHERE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define US_ABI_VERSION 1
+
+/* exported from libultrasphere_b200.so (everything else in the library is hidden) */
+#if defined(__GNUC__)
+#define US_API __attribute__((visibility("default")))
+#else
+#define US_API
+#endif
+
+/* capacity of one compiled tree (kernel-parameter resident, "constant memory") */
+#define US_MAX_NODES 256 /* internal nodes = angles (s_ndim) */
+#define US_MAX_LEAVES (US_MAX_NODES + 1)
+#define US_MAX_DIMS 12   /* broadcast dims of the strided path after collapsing */
+#define US_MAX_STACK 64  /* pending `c` branches of the pre-order program */
+#define US_MAX_AXES 64   /* axes per us_separable_reduce call */
+
+/* element types (the path computes in the type it is given) */
+#define US_F32 0
+#define US_F64 1
+
+/* library error codes (negative; positive values are cudaError_t) */
+#define US_EINVAL (-1)   /* bad argument (null pointer, bad dtype, bad sizes) */
+#define US_ECAPACITY (-2) /* tree / dims exceed the US_MAX_* capacities */
+#define US_EPLAN (-3)    /* malformed branching expression or plan */
+
+/* node kinds of the pre-order program == reference BranchingType (_coordinates.py:16-26) */
+#define US_NODE_A 0  /* cos child leaf, sin child leaf */
+#define US_NODE_B 1  /* cos child leaf, sin child internal */
+#define US_NODE_BP 2 /* cos child internal, sin child leaf */
+#define US_NODE_C 3  /* both internal */
+
+/*
+ * A compiled coordinate tree.  node[i] describes the i-th internal node in PRE-ORDER with the
+ * cos subtree before the sin subtree — the order of `branching_types_expression`
+ * (_coordinates.py:206-242).  In that order a `c` node defers its sin branch on a stack and an
+ * `a` node resumes the most recently deferred branch, so a running product (to_cartesian) or a
+ * running norm (from_cartesian, walked backwards) needs a stack only at `c`/`a` nodes.
+ *
+ *   bits  0..1   kind (US_NODE_*)
+ *   bits  8..23  angle slot  = position of this node in `s_nodes`  (pointer-table index)
+ *   bits 24..39  cos leaf    = position of the cos child in `c_nodes`, 0xFFFF if internal
+ *   bits 40..55  sin leaf    = position of the sin child in `c_nodes`, 0xFFFF if internal
+ */
+typedef struct us_plan {
+  int32_t n_nodes;   /* s_ndim */
+  int32_t n_leaves;  /* c_ndim = n_nodes + 1 */
+  int32_t max_stack; /* deepest deferred-branch stack the program needs */
+  int32_t reserved;
+  uint64_t node[US_MAX_NODES];
+} us_plan_t;
+
+#define US_NO_LEAF 0xFFFFu
+
+US_API int us_abi_version(void);
+US_API const char* us_version(void);
+US_API const char* us_last_error_string(void);
+
+/* Number of CUDA devices visible (>= 0), or minus the cudaError_t that the query raised. */
+US_API int us_device_count(void);
+
+/*
+ * Compile a branching-type expression.  kinds[i] in pre-order; angle_slot[i] = index of node i
+ * in s_nodes; leaf_slot[j] = index in c_nodes of the j-th leaf OPERAND in program order (node by
+ * node, a node's cos operand before its sin operand: `a` consumes two entries, `b` and `b'` one,
+ * `c` none).  Validates that the expression closes exactly (what _creation.py:66-70 raises
+ * ValueError for) and that slots are permutations.
+ */
+US_API int us_plan_compile(int32_t n_nodes, const uint8_t* kinds, const int32_t* angle_slot,
+                    const int32_t* leaf_slot, us_plan_t* out_plan);
+
+/*
+ * x_leaf = r * prod over the root→leaf path of cos(theta) or sin(theta)   (multiply order
+ * root→leaf, one rounding per product — _coordinates.py:645-648).
+ *
+ * The launch covers `n` points laid out as a C-contiguous index space shape[0..ndim).
+ * Input k contributes the element at offset sum_d idx_d * stride_k,d where stride is the
+ * dense stride of the sub-shape selected by mask bit d (bit d set = the input spans dim d,
+ * clear = broadcast along d).  ndim==1 with all masks 1 is the contiguous fast path.
+ *
+ * angle_dev[s]  : n_nodes pointers, s_nodes order         r_dev : may be NULL (r = 1)
+ * out_dev[l]    : n_leaves pointers, c_nodes order, each n elements; NULL entries are skipped
+ */
+US_API int us_to_cartesian(const us_plan_t* plan, int dtype, int64_t n, int ndim, const int64_t* shape,
+                    const void* const* angle_dev, const uint32_t* angle_mask, const void* r_dev,
+                    uint32_t r_mask, void* const* out_dev, void* stream);
+
+/*
+ * r = sqrt(sum over leaves in c_nodes order of x^2)  (sequential, each square and each add
+ * rounded once — bit-identical to numpy.linalg.vector_norm(axis=0), _coordinates.py:556-563);
+ * per internal node, children first: theta = atan2(v_sin, v_cos), v = sqrt(v_sin^2 + v_cos^2)
+ * (_coordinates.py:575-578).
+ *
+ * x_dev[l]         : n_leaves pointers, c_nodes order (+ masks as above)
+ * r_out_dev        : n elements or NULL
+ * angle_out_dev[s] : n_nodes pointers, s_nodes order, each n elements; NULL entries skipped
+ */
+US_API int us_from_cartesian(const us_plan_t* plan, int dtype, int64_t n, int ndim, const int64_t* shape,
+                      const void* const* x_dev, const uint32_t* x_mask, void* r_out_dev,
+                      void* const* angle_out_dev, void* stream);
+
+/*
+ * out[m] (+)= sum over the grid of  prod_i w_i[idx_i] * val[idx_0, ..., idx_{ndim-1}, m]
+ * val is C-contiguous with shape (extent[0..ndim), m); w_dev[i] has extent[i] entries (an axis
+ * the integrand did not depend on arrives with extent 1 and w = sum of that axis' weights,
+ * _integral.py:272-273).  Complex values are passed as m*2 reals (weights are real).
+ * Accumulation is in float64 whatever `dtype` is; the cross-block order is fixed (deterministic).
+ * scratch_dev: at least us_weighted_reduce_scratch_bytes(m) bytes, 16-byte aligned.
+ */
+US_API int64_t us_weighted_reduce_scratch_bytes(int64_t m);
+US_API int us_weighted_reduce(int dtype, int ndim, const int64_t* extent, const void* const* w_dev,
+                       const void* val_dev, int64_t m, void* out_dev, int accumulate,
+                       void* scratch_dev, int64_t scratch_bytes, void* stream);
+
+/*
+ * For every axis a < n_axes:  out_a[m] = sum_j w_a[j] * val_a[j, m]   (val_a: (len[a], m[a])
+ * C-contiguous).  One launch for all axes.  _integral.py:245-260.
+ */
+US_API int us_separable_reduce(int dtype, int n_axes, const int64_t* len, const int64_t* m,
+                        const void* const* w_dev, const void* const* val_dev,
+                        void* const* out_dev, void* stream);
+
+/*
+ * Measurement helper: runs a dependent-free DFMA (dtype=US_F64) or FFMA (US_F32) loop on every
+ * SM and returns the achieved TFLOP/s in *tflops (this one call synchronises).  Used by bench.py
+ * as the denominator for the FP64-pipe-bound kernels (MEASURED_PEAKS.json has no FP64 entry).
+ */
+US_API int us_probe_fma_peak(int dtype, int iters, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ULTRASPHERE_B200_H */

@@ -1,0 +1,199 @@
+"""Host-side logic of the product package, checked on the CPU: factories and node orders against
+the golden tree dump, the tree compiler through a NumPy emulation of the kernel's walk, the
+launch-geometry (broadcast mask) logic, the C ABI surface, and the "no CPU fallback" errors."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import ultrasphere_b200 as us
+from oracle import vks_oracle as vo
+from tests.helpers import emulate_from_cartesian, emulate_to_cartesian, load_trees, make
+from ultrasphere_b200 import _native
+from ultrasphere_b200._plan import plan_for
+from ultrasphere_b200._transform import _Geometry
+
+TREES = load_trees()
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("spec", sorted(TREES))
+def test_factories_match_reference_dump(spec):
+    c = make(us, spec)
+    g = TREES[spec]
+    assert list(c.s_nodes) == g["s_nodes"]
+    assert list(c.c_nodes) == g["c_nodes"]
+    assert [list(e) for e in c.cos_edges] == g["cos_edges"]
+    assert [list(e) for e in c.sin_edges] == g["sin_edges"]
+    assert [[k, v.value] for k, v in c.branching_types.items()] == g["branching_types"]
+    assert [[k, (None if v != v else int(v))] for k, v in c.S.items()] == g["S"]
+    assert c.root == g["root"] and list(c.G.nodes) == g["G_nodes"]
+    assert (c.s_ndim, c.c_ndim) == (g["s_ndim"], g["c_ndim"])
+    if c.s_ndim > 0:
+        assert repr(c) == g["repr"] and str(c) == g["repr"]
+        assert c.branching_types_expression_str == g["expression_str"]
+        assert c.root_index == 0
+
+
+# reference tests/test_creation.py:11-21
+@pytest.mark.parametrize("s_ndim", [0, 1, 2, 3, 6, 103])
+def test_generate(s_ndim):
+    assert us.create_random(s_ndim).s_ndim == s_ndim
+    assert us.create_standard(s_ndim).s_ndim == s_ndim
+    assert us.create_standard_prime(s_ndim).s_ndim == s_ndim
+
+
+@pytest.mark.parametrize("q", [0, 1, 2, 5])
+def test_generate_hopf(q):
+    assert us.create_hopf(q).c_ndim == 2**q
+
+
+def test_bad_expressions_raise_value_error():
+    for expr in ("x", "ab", "aa", "b", "ca", "bq"):
+        with pytest.raises(ValueError):
+            us.create_from_branching_types(expr)
+    with pytest.raises(ValueError):
+        us.create_hopf(-1)
+
+
+def test_identity_semantics_and_pickle():
+    import pickle
+
+    a, b = us.create_standard(3), us.create_standard(3)
+    assert a != b and a == a and hash(a) == hash(a)  # identity of G, as in the reference
+    c = pickle.loads(pickle.dumps(us.create_hopf(2)))
+    assert repr(c) == "SphericalCoordinates(caa)" and c.c_nodes == [0, 1, 2, 3]
+    assert us.get_child(a.G, "theta0", "sin") == "theta1" and us.get_parent(a.G, "theta1") == "theta0"
+    assert us.get_parent(a.G, "theta0") is None
+    assert a.is_c_keys_range and not a.is_s_keys_range
+    assert abs(us.create_standard(2).surface_area() - 4 * np.pi) < 1e-12
+    assert abs(us.create_standard(2).volume() - 4 * np.pi / 3) < 1e-12
+
+
+PLAN_SPECS = [s for s in sorted(TREES) if TREES[s]["s_ndim"] > 0]
+
+
+@pytest.mark.parametrize("spec", PLAN_SPECS)
+def test_compiled_program_reproduces_oracle(spec):
+    """The pre-order program, walked the way the kernels walk it, gives the oracle's numbers:
+    bit-exact (same NumPy ufuncs, same association), so any mismatch is a tree-compiler bug."""
+    c = make(us, spec)
+    t = vo.make(spec)
+    ct = plan_for(c)
+    assert ct.n_nodes == c.s_ndim and ct.n_leaves == c.c_ndim
+    rng = np.random.default_rng(5)
+    for dt in (np.float64, np.float32):
+        x = rng.uniform(-1, 1, (c.c_ndim, 33)).astype(dt)
+        want = vo.from_cartesian(t, x)
+        r, ang = emulate_from_cartesian(ct, list(x))
+        assert np.array_equal(r, want["r"])
+        for i, node in enumerate(c.s_nodes):
+            assert np.array_equal(ang[i], want[node]), (spec, node)
+        sph = {node: ang[i] for i, node in enumerate(c.s_nodes)} | {"r": r}
+        cart = emulate_to_cartesian(ct, ang, r)
+        wantc = vo.to_cartesian(t, sph)
+        for i, leaf in enumerate(c.c_nodes):
+            assert np.array_equal(cart[i], wantc[leaf]), (spec, leaf)
+    # structure tables used for output shapes
+    for li, leaf in enumerate(c.c_nodes):
+        anc = []
+        node = leaf
+        while us.get_parent(c.G, node) is not None:
+            node = us.get_parent(c.G, node)
+            anc.append(c.s_nodes.index(node))
+        assert list(ct.leaf_ancestors[li]) == anc
+
+
+def test_plan_capacity_and_validation():
+    with pytest.raises(ValueError):
+        plan_for(us.create_standard(_native.US_MAX_NODES + 1))
+    assert plan_for(us.create_standard(_native.US_MAX_NODES)).n_nodes == _native.US_MAX_NODES
+    # a c-chain deeper than the deferred-branch stack is refused, not silently mis-run
+    deep = "c" * (_native.US_MAX_STACK + 1) + "a" * (_native.US_MAX_STACK + 2)
+    with pytest.raises(ValueError):
+        plan_for(us.create_from_branching_types(deep))
+    ok = "c" * _native.US_MAX_STACK + "a" * (_native.US_MAX_STACK + 1)
+    assert plan_for(us.create_from_branching_types(ok)).max_stack == _native.US_MAX_STACK
+    lib = _native.lib()
+    plan = _native.UsPlan()
+    kinds = (ctypes.c_uint8 * 2)(1, 1)  # "bb" never closes
+    slots = (ctypes.c_int32 * 2)(0, 1)
+    leaves = (ctypes.c_int32 * 3)(0, 1, 2)
+    assert lib.us_plan_compile(2, kinds, slots, leaves, ctypes.byref(plan)) == -3
+    assert b"close" in lib.us_last_error_string()
+
+
+def test_library_exports_every_declared_symbol():
+    """include/ultrasphere_b200.h is the contract: every US_API function must be in the .so."""
+    with open(os.path.join(ROOT, "include", "ultrasphere_b200.h")) as fh:
+        header = fh.read()
+    declared = set(re.findall(r"US_API\s+[\w\s\*]+?\b(us_\w+)\s*\(", header))
+    assert declared == set(_native.EXPORTED), declared ^ set(_native.EXPORTED)
+    lib = _native.lib()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.us_abi_version() == _native.US_ABI_VERSION
+    assert b"sm_100a" in lib.us_version()
+    assert ctypes.sizeof(_native.UsPlan) == 16 + 8 * _native.US_MAX_NODES
+    assert lib.us_weighted_reduce_scratch_bytes(3) >= 3 * 8
+
+
+def test_argument_errors_do_not_need_a_gpu():
+    lib = _native.lib()
+    assert lib.us_to_cartesian(None, 0, 0, 1, None, None, None, None, 0, None, None) == -1
+    assert b"null plan" in lib.us_last_error_string()
+    assert lib.us_weighted_reduce(7, 1, None, None, None, 1, None, 0, None, 0, None) == -1
+    assert lib.us_separable_reduce(0, 0, None, None, None, None, None, None) == -2
+
+
+def test_no_cpu_fallback():
+    c = us.create_spherical()
+    with pytest.raises(TypeError):
+        c.from_cartesian(np.asarray([1.0, 2.0, 3.0]))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        c.from_cartesian(torch.ones(3, 4))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        c.to_cartesian({"theta": torch.ones(2), "phi": torch.ones(2)})
+    with pytest.raises(KeyError):
+        c.to_cartesian({"theta": torch.ones(2)})
+    with pytest.raises(TypeError):
+        us.roots(c, 4, expand_dims_x=True, xp=np)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        us.integrate(c, lambda s: s["theta"], False, 4, xp=torch, device="cpu")
+
+
+def test_zero_angle_tree_passthrough():
+    c = us.create_standard(0)
+    x = torch.tensor([-2.0, 3.0])
+    assert c.from_cartesian({"theta0": x})["r"] is x  # no abs, like the reference
+    assert c.to_cartesian({"r": x})["theta0"] is x
+
+
+def test_launch_geometry_masks():
+    n = 5
+    xs = [torch.zeros(n, 1, 1), torch.zeros(1, n, 1), torch.zeros(1, 1, 2 * n)]
+    geo = _Geometry(list(xs) + [None], (n, n, 2 * n))
+    assert geo.shape == [n, n, 2 * n] and geo.masks == [0b001, 0b010, 0b100, 0]
+    # equal dense shapes collapse to one dimension
+    same = [torch.zeros(2, 3, 4) for _ in range(3)]
+    geo = _Geometry(same, (2, 3, 4))
+    assert geo.shape == [24] and geo.masks == [1, 1, 1]
+    # a 0-d operand next to dense ones is a pure broadcast
+    geo = _Geometry([torch.zeros(2, 3), torch.zeros(())], (2, 3))
+    assert geo.shape == [6] and geo.masks == [1, 0]
+    # expanded (stride-0) operands are recognised as broadcasts without a copy
+    base = torch.zeros(4, 1)
+    geo = _Geometry([base.expand(4, 6), torch.zeros(4, 6)], (4, 6))
+    assert geo.masks == [0b01, 0b11] and geo.tensors[0].data_ptr() == base.data_ptr()
+    # a transposed view is densified (one copy), adjacent dims that all operands share merge
+    t = torch.arange(12.0).reshape(3, 4).t()
+    geo = _Geometry([t, torch.zeros(4, 3)], (4, 3))
+    assert geo.shape == [12] and geo.tensors[0].is_contiguous()
+    # more independent axes than the parameter block holds: densified instead of failing
+    k = _native.US_MAX_DIMS + 1
+    ops = [torch.zeros((1,) * i + (2,) + (1,) * (k - i - 1)) for i in range(k)]
+    geo = _Geometry(ops, (2,) * k)
+    assert geo.shape == [2**k] and all(m == 1 for m in geo.masks)

@@ -1,0 +1,344 @@
+"""Host glue of the transforms: dict-of-tensors ⇄ pointer tables ⇄ one kernel launch.
+
+Semantics follow /root/reference/src/ultrasphere/_coordinates.py:555-579 (``from_cartesian``) and
+:636-656 (``to_cartesian``): key orders, per-entry broadcast shapes, ``r`` defaulting to 1,
+``KeyError`` for a missing node, array input indexed by leaf id.  The array work is done by
+``us_to_cartesian`` / ``us_from_cartesian`` (include/ultrasphere_b200.h) on the caller's current
+CUDA stream; outputs are fresh tensors that never alias the inputs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections.abc import Mapping, Sequence
+from typing import Any
+
+import torch
+
+from . import _native
+from ._coordinates import SphericalCoordinates
+from ._plan import CompiledTree, plan_for
+
+_DTYPE_CODE = {torch.float32: _native.US_F32, torch.float64: _native.US_F64}
+
+
+def _require_cuda_tensors(values: Sequence[Any], what: str) -> torch.device:
+    device: torch.device | None = None
+    for v in values:
+        if not isinstance(v, torch.Tensor):
+            raise TypeError(
+                f"{what}: expected CUDA torch.Tensor values, got {type(v).__name__}; "
+                "ultrasphere_b200 has no NumPy / CPU path"
+            )
+        if v.device.type != "cuda":
+            raise RuntimeError(
+                f"{what}: tensor on {v.device}; ultrasphere_b200 runs on CUDA devices only (no CPU fallback)"
+            )
+        if device is None:
+            device = v.device
+        elif v.device != device:
+            raise RuntimeError(f"{what}: tensors on different devices ({device} and {v.device})")
+    assert device is not None
+    return device
+
+
+def _compute_dtype(tensors: Sequence[torch.Tensor]) -> torch.dtype:
+    dt = tensors[0].dtype
+    for t in tensors[1:]:
+        if t.dtype != dt:
+            dt = torch.promote_types(dt, t.dtype)
+    if not dt.is_floating_point:
+        if dt.is_complex:
+            raise TypeError("complex coordinates are not supported")
+        dt = torch.get_default_dtype()
+    if dt not in _DTYPE_CODE:
+        raise TypeError(f"unsupported dtype {dt}: the kernels compute in float32 or float64")
+    return dt
+
+
+class _Geometry:
+    """Launch index space plus, for every operand, its dense-broadcast mask."""
+
+    __slots__ = ("full_shape", "n", "shape", "masks", "tensors")
+
+    def __init__(self, tensors: list[torch.Tensor | None], full_shape: tuple[int, ...]):
+        self.full_shape = full_shape
+        n = 1
+        for e in full_shape:
+            n *= e
+        self.n = n
+        live = [t for t in tensors if t is not None]
+        # fast path: everything already dense over the full shape
+        if all(t.shape == full_shape and t.is_contiguous() for t in live):
+            self.shape = [n]
+            self.masks = [0 if t is None else 1 for t in tensors]
+            self.tensors = tensors
+            return
+        nd = len(full_shape)
+        spans: list[list[bool] | None] = []
+        fixed: list[torch.Tensor | None] = []
+        for t in tensors:
+            if t is None:
+                spans.append(None)
+                fixed.append(None)
+                continue
+            t, sp = _span_of(t, nd)
+            spans.append(sp)
+            fixed.append(t)
+        # drop unit dims, merge neighbours that every operand treats alike
+        dims = [d for d in range(nd) if full_shape[d] != 1]
+        shape: list[int] = []
+        groups: list[list[int]] = []
+        for d in dims:
+            if groups and all(sp is None or sp[groups[-1][-1]] == sp[d] for sp in spans):
+                groups[-1].append(d)
+                shape[-1] *= full_shape[d]
+            else:
+                groups.append([d])
+                shape.append(full_shape[d])
+        if not shape:
+            shape, groups = [1], [[]]
+        if len(shape) > _native.US_MAX_DIMS:
+            # too many independent broadcast axes for the parameter block: densify on the device
+            fixed = [None if t is None else t.expand(full_shape).contiguous() for t in fixed]
+            self.shape = [n]
+            self.masks = [0 if t is None else 1 for t in fixed]
+            self.tensors = fixed
+            return
+        masks = []
+        for sp in spans:
+            m = 0
+            if sp is not None:
+                for gi, g in enumerate(groups):
+                    if g and sp[g[0]]:
+                        m |= 1 << gi
+            masks.append(m)
+        self.shape = shape
+        self.masks = masks
+        self.tensors = fixed
+
+
+def _span_of(t: torch.Tensor, nd: int) -> tuple[torch.Tensor, list[bool]]:
+    """Which launch dims does ``t`` really vary along, and is it dense over exactly those?"""
+    pad = nd - t.dim()
+    for _ in range(2):
+        sp = [False] * nd
+        expect = 1
+        dense = True
+        for d in range(t.dim() - 1, -1, -1):
+            size, stride = t.shape[d], t.stride(d)
+            if size == 1 or stride == 0:
+                continue
+            sp[pad + d] = True
+            if stride != expect:
+                dense = False
+                break
+            expect *= size
+        if dense:
+            return t, sp
+        t = t.contiguous()  # arbitrary strided view: one device-side copy, then dense
+    raise AssertionError("contiguous tensor must be dense")
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class _NoGuard:
+    def __enter__(self) -> None:
+        return None
+
+    def __exit__(self, *exc: Any) -> None:
+        return None
+
+
+_NO_GUARD = _NoGuard()
+
+
+def device_guard(device: torch.device) -> Any:
+    """Make ``device`` current for the launch (the library launches on the calling thread's
+    current device); free when it already is."""
+    if device.index is None or device.index == torch.cuda.current_device():
+        return _NO_GUARD
+    return torch.cuda.device(device)
+
+
+def _ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+# --------------------------------------------------------------------------------------
+# to_cartesian
+# --------------------------------------------------------------------------------------
+def to_cartesian(c: SphericalCoordinates[Any, Any], spherical: Mapping[Any, Any], *, as_array: bool = False) -> Any:
+    angles_in = [spherical[k] for k in c.s_nodes]  # KeyError for a missing angle
+    r_in = spherical.get("r", 1)
+    if c.s_ndim == 0:
+        # a single leaf that is also the root: x = r  
+        if as_array:
+            if not isinstance(r_in, torch.Tensor):
+                raise TypeError("to_cartesian(as_array=True) on a 0-angle tree needs a tensor r")
+            return torch.stack([r_in], dim=0)
+        return {c.c_nodes[0]: r_in}
+    r_is_tensor = isinstance(r_in, torch.Tensor)
+    device = _require_cuda_tensors(angles_in + ([r_in] if r_is_tensor else []), "to_cartesian")
+    dtype = _compute_dtype(angles_in + ([r_in] if r_is_tensor else []))
+    if not r_is_tensor:
+        if isinstance(r_in, complex):
+            raise TypeError("complex r is not supported")
+        if r_in == 1:
+            r_in = None
+        else:
+            r_in = torch.full((), float(r_in), dtype=dtype, device=device)
+    angles = [a if a.dtype == dtype else a.to(dtype) for a in angles_in]
+    r = None if r_in is None else (r_in if r_in.dtype == dtype else r_in.to(dtype))
+    ct = plan_for(c)
+
+    r_shape = tuple(r.shape) if r is not None else ()
+    shapes = [tuple(a.shape) for a in angles]
+    same = all(s == shapes[0] for s in shapes) and (r is None or r_shape == shapes[0] or r_shape == ())
+    if same or as_array:
+        full = shapes[0] if same else torch.broadcast_shapes(r_shape, *shapes)
+        out = _launch_to(ct, device, dtype, angles, r, full, list(range(ct.n_leaves)))
+        if as_array:
+            return out
+        return {leaf: out[i] for i, leaf in enumerate(c.c_nodes)}
+    # heterogeneous shapes: every leaf keeps the broadcast shape of r and its own ancestors
+    leaf_shapes = [
+        torch.broadcast_shapes(r_shape, *[shapes[a] for a in ct.leaf_ancestors[l]]) for l in range(ct.n_leaves)
+    ]
+    result: dict[int, torch.Tensor] = {}
+    for shape in dict.fromkeys(leaf_shapes):
+        members = [l for l in range(ct.n_leaves) if leaf_shapes[l] == shape]
+        out = _launch_to(ct, device, dtype, angles, r, tuple(shape), members)
+        for j, l in enumerate(members):
+            result[l] = out[j]
+    return {leaf: result[i] for i, leaf in enumerate(c.c_nodes)}
+
+
+def _launch_to(
+    ct: CompiledTree,
+    device: torch.device,
+    dtype: torch.dtype,
+    angles: list[torch.Tensor],
+    r: torch.Tensor | None,
+    full: tuple[int, ...],
+    members: list[int],
+) -> torch.Tensor:
+    """One launch over ``full``; returns a ``(len(members), *full)`` tensor (rows = member leaves)."""
+    needed = set()
+    for l in members:
+        needed.update(ct.leaf_ancestors[l])
+    # angles that feed none of the requested leaves are read at element 0 and their value unused
+    ops: list[torch.Tensor | None] = [a if i in needed else None for i, a in enumerate(angles)]
+    geo = _Geometry(ops + [r], full)
+    out = torch.empty((len(members), *full), dtype=dtype, device=device)
+    if geo.n == 0:
+        return out
+    in_ptrs = []
+    for i, t in enumerate(geo.tensors[:-1]):
+        in_ptrs.append(angles[i].data_ptr() if t is None else t.data_ptr())
+    out_ptrs: list[int | None] = [None] * ct.n_leaves
+    row_bytes = geo.n * out.element_size()
+    base = out.data_ptr()
+    for j, l in enumerate(members):
+        out_ptrs[l] = base + j * row_bytes
+    rt = geo.tensors[-1]
+    with device_guard(device):
+        status = _native.lib().us_to_cartesian(
+            C.byref(ct.plan),
+            _DTYPE_CODE[dtype],
+            geo.n,
+            len(geo.shape),
+            _native.i64_array(geo.shape),
+            _native.void_p_array(in_ptrs),
+            _native.u32_array(geo.masks[:-1]),
+            _ptr(rt),
+            geo.masks[-1],
+            _native.void_p_array(out_ptrs),
+            _stream_ptr(device),
+        )
+    _native.check(status, "us_to_cartesian")
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# from_cartesian
+# --------------------------------------------------------------------------------------
+def from_cartesian(c: SphericalCoordinates[Any, Any], cartesian: Any) -> dict[Any, Any]:
+    leaves_in = [cartesian[k] for k in c.c_nodes]  # mapping, or a tensor indexed by leaf id
+    if c.s_ndim == 0:
+        return {"r": leaves_in[0]}
+    device = _require_cuda_tensors(leaves_in, "from_cartesian")
+    dtype = _compute_dtype(leaves_in)
+    leaves = [x if x.dtype == dtype else x.to(dtype) for x in leaves_in]
+    ct = plan_for(c)
+    shapes = [tuple(x.shape) for x in leaves]
+    order = list(reversed(range(ct.n_nodes)))  # dict order: "r", then children before parents
+    if all(s == shapes[0] for s in shapes):
+        out = _launch_from(ct, device, dtype, leaves, shapes[0], True, list(range(ct.n_nodes)))
+        result: dict[Any, Any] = {"r": out[0]}
+        for s in order:
+            result[c.s_nodes[s]] = out[1 + s]
+        return result
+    full = tuple(torch.broadcast_shapes(*shapes))
+    node_shapes = [tuple(torch.broadcast_shapes(*[shapes[l] for l in ct.angle_leaves[s]])) for s in range(ct.n_nodes)]
+    got: dict[int, torch.Tensor] = {}
+    r_out: torch.Tensor | None = None
+    for shape in dict.fromkeys([full] + node_shapes):
+        members = [s for s in range(ct.n_nodes) if node_shapes[s] == shape]
+        want_r = shape == full and r_out is None
+        out = _launch_from(ct, device, dtype, leaves, shape, want_r, members)
+        if want_r:
+            r_out = out[0]
+        for j, s in enumerate(members):
+            got[s] = out[(1 if want_r else 0) + j]
+    result = {"r": r_out}
+    for s in order:
+        result[c.s_nodes[s]] = got[s]
+    return result
+
+
+def _launch_from(
+    ct: CompiledTree,
+    device: torch.device,
+    dtype: torch.dtype,
+    leaves: list[torch.Tensor],
+    full: tuple[int, ...],
+    want_r: bool,
+    members: list[int],
+) -> torch.Tensor:
+    """One launch over ``full``; returns ``(want_r + len(members), *full)``: r first, then the
+    member angles in the given order."""
+    if want_r:
+        needed = set(range(ct.n_leaves))
+    else:
+        needed = set()
+        for s in members:
+            needed.update(ct.angle_leaves[s])
+    ops: list[torch.Tensor | None] = [x if i in needed else None for i, x in enumerate(leaves)]
+    geo = _Geometry(ops, full)
+    rows = (1 if want_r else 0) + len(members)
+    out = torch.empty((rows, *full), dtype=dtype, device=device)
+    if geo.n == 0:
+        return out
+    in_ptrs = [leaves[i].data_ptr() if t is None else t.data_ptr() for i, t in enumerate(geo.tensors)]
+    row_bytes = geo.n * out.element_size()
+    base = out.data_ptr()
+    out_ptrs: list[int | None] = [None] * ct.n_nodes
+    for j, s in enumerate(members):
+        out_ptrs[s] = base + ((1 if want_r else 0) + j) * row_bytes
+    with device_guard(device):
+        status = _native.lib().us_from_cartesian(
+            C.byref(ct.plan),
+            _DTYPE_CODE[dtype],
+            geo.n,
+            len(geo.shape),
+            _native.i64_array(geo.shape),
+            _native.void_p_array(in_ptrs),
+            _native.u32_array(geo.masks),
+            base if want_r else None,
+            _native.void_p_array(out_ptrs),
+            _stream_ptr(device),
+        )
+    _native.check(status, "us_from_cartesian")
+    return out

@@ -1,0 +1,218 @@
+// C ABI entry points (include/ultrasphere_b200.h): argument checking, plan compilation,
+// dispatch between the tiled fast path and the strided path, error reporting.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "us_common.cuh"
+#include "us_params.cuh"
+
+namespace us {
+
+static thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* where) {
+  snprintf(g_err, sizeof g_err, "%s: %s (%s)", where, cudaGetErrorString(e), cudaGetErrorName(e));
+  return (int)e;
+}
+
+static int check_plan(const us_plan_t* plan, const char* who) {
+  if (!plan) return fail(US_EINVAL, "%s: null plan", who);
+  if (plan->n_nodes < 1 || plan->n_nodes > US_MAX_NODES || plan->n_leaves != plan->n_nodes + 1)
+    return fail(US_EPLAN, "%s: plan has %d nodes / %d leaves", who, plan->n_nodes, plan->n_leaves);
+  if (plan->max_stack < 0 || plan->max_stack > US_MAX_STACK)
+    return fail(US_ECAPACITY, "%s: plan needs a stack of %d > %d", who, plan->max_stack, US_MAX_STACK);
+  return 0;
+}
+
+static int fill_common(XformParams& p, const us_plan_t* plan, int dtype, int64_t n, int ndim,
+                       const int64_t* shape, const char* who) {
+  if (int rc = check_plan(plan, who)) return rc;
+  if (dtype != US_F32 && dtype != US_F64) return fail(US_EINVAL, "%s: bad dtype %d", who, dtype);
+  if (n < 0) return fail(US_EINVAL, "%s: n < 0", who);
+  if (ndim < 1 || ndim > US_MAX_DIMS) return fail(US_ECAPACITY, "%s: ndim %d not in 1..%d", who, ndim, US_MAX_DIMS);
+  if (!shape) return fail(US_EINVAL, "%s: null shape", who);
+  int64_t prod = 1;
+  for (int d = 0; d < ndim; ++d) {
+    if (shape[d] < 0) return fail(US_EINVAL, "%s: negative extent", who);
+    p.shape[d] = shape[d];
+    prod *= shape[d];
+  }
+  if (prod != n) return fail(US_EINVAL, "%s: shape product %lld != n %lld", who, (long long)prod, (long long)n);
+  memcpy(&p.plan, plan, sizeof(us_plan_t));
+  p.ndim = ndim;
+  p.n = n;
+  return 0;
+}
+
+}  // namespace us
+
+using namespace us;
+
+extern "C" int us_abi_version(void) { return US_ABI_VERSION; }
+extern "C" const char* us_version(void) { return "ultrasphere_b200 0.1.0 (sm_100a)"; }
+extern "C" const char* us_last_error_string(void) { return g_err; }
+
+extern "C" int us_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) return -cuda_fail(e, "cudaGetDeviceCount");
+  return n;
+}
+
+extern "C" int us_plan_compile(int32_t n_nodes, const uint8_t* kinds, const int32_t* angle_slot,
+                               const int32_t* leaf_slot, us_plan_t* out) {
+  if (!out) return fail(US_EINVAL, "us_plan_compile: null output");
+  if (n_nodes < 1) return fail(US_EPLAN, "us_plan_compile: a tree needs at least one internal node");
+  if (n_nodes > US_MAX_NODES)
+    return fail(US_ECAPACITY, "us_plan_compile: %d internal nodes exceed the capacity of %d", n_nodes, US_MAX_NODES);
+  if (!kinds || !angle_slot || !leaf_slot) return fail(US_EINVAL, "us_plan_compile: null table");
+  memset(out, 0, sizeof *out);
+  bool seen_slot[US_MAX_NODES] = {false};
+  bool seen_leaf[US_MAX_LEAVES] = {false};
+  int open_branches = 1;  // subtrees still to be written, the root first
+  int sp = 0, max_sp = 0, li = 0;
+  const int n_leaves = n_nodes + 1;
+  for (int i = 0; i < n_nodes; ++i) {
+    const int k = kinds[i];
+    if (k < 0 || k > 3) return fail(US_EPLAN, "us_plan_compile: node %d has invalid kind %d", i, k);
+    if (open_branches < 1) return fail(US_EPLAN, "us_plan_compile: expression closes before node %d", i);
+    const int s = angle_slot[i];
+    if (s < 0 || s >= n_nodes || seen_slot[s]) return fail(US_EPLAN, "us_plan_compile: bad or repeated angle slot %d", s);
+    seen_slot[s] = true;
+    uint32_t lc = US_NO_LEAF, ls = US_NO_LEAF;
+    if (k == US_NODE_A || k == US_NODE_B) {
+      if (li >= n_leaves) return fail(US_EPLAN, "us_plan_compile: too many leaf operands");
+      lc = (uint32_t)leaf_slot[li++];
+    }
+    if (k == US_NODE_A || k == US_NODE_BP) {
+      if (li >= n_leaves) return fail(US_EPLAN, "us_plan_compile: too many leaf operands");
+      ls = (uint32_t)leaf_slot[li++];
+    }
+    for (uint32_t l : {lc, ls}) {
+      if (l == US_NO_LEAF) continue;
+      if (l >= (uint32_t)n_leaves || seen_leaf[l]) return fail(US_EPLAN, "us_plan_compile: bad or repeated leaf slot %u", l);
+      seen_leaf[l] = true;
+    }
+    open_branches += (k == US_NODE_C) ? 1 : (k == US_NODE_A ? -1 : 0);
+    if (k == US_NODE_C) {
+      if (++sp > max_sp) max_sp = sp;
+    } else if (k == US_NODE_A && i != n_nodes - 1) {
+      if (sp < 1) return fail(US_EPLAN, "us_plan_compile: `a` at node %d has no deferred branch to resume", i);
+      --sp;
+    }
+    out->node[i] = (uint64_t)k | ((uint64_t)(uint32_t)s << 8) | ((uint64_t)lc << 24) | ((uint64_t)ls << 40);
+  }
+  if (open_branches != 0 || sp != 0 || li != n_leaves)
+    return fail(US_EPLAN, "us_plan_compile: expression does not close (open=%d, stack=%d, leaves=%d/%d)",
+                open_branches, sp, li, n_leaves);
+  if (max_sp > US_MAX_STACK)
+    return fail(US_ECAPACITY, "us_plan_compile: deferred-branch depth %d exceeds %d", max_sp, US_MAX_STACK);
+  out->n_nodes = n_nodes;
+  out->n_leaves = n_leaves;
+  out->max_stack = max_sp;
+  return 0;
+}
+
+extern "C" int us_to_cartesian(const us_plan_t* plan, int dtype, int64_t n, int ndim, const int64_t* shape,
+                               const void* const* angle_dev, const uint32_t* angle_mask, const void* r_dev,
+                               uint32_t r_mask, void* const* out_dev, void* stream) {
+  static const char* who = "us_to_cartesian";
+  XformParams p;
+  memset(&p, 0, sizeof p);
+  if (int rc = fill_common(p, plan, dtype, n, ndim, shape, who)) return rc;
+  if (!angle_dev || !angle_mask || !out_dev) return fail(US_EINVAL, "%s: null pointer table", who);
+  for (int s = 0; s < plan->n_nodes; ++s) {
+    if (!angle_dev[s] && n > 0) return fail(US_EINVAL, "%s: angle %d is null", who, s);
+    p.in[s] = angle_dev[s];
+    p.in_mask[s] = angle_mask[s];
+  }
+  for (int l = 0; l < plan->n_leaves; ++l) p.out[l] = out_dev[l];
+  p.r_in = r_dev;
+  p.r_mask = r_mask;
+  if (n == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = try_launch_to_cartesian_tiled(p, dtype, st);
+  if (rc == 1) return 0;
+  if (rc != 0) return rc;
+  return launch_to_cartesian_strided(p, dtype, st);
+}
+
+extern "C" int us_from_cartesian(const us_plan_t* plan, int dtype, int64_t n, int ndim, const int64_t* shape,
+                                 const void* const* x_dev, const uint32_t* x_mask, void* r_out_dev,
+                                 void* const* angle_out_dev, void* stream) {
+  static const char* who = "us_from_cartesian";
+  XformParams p;
+  memset(&p, 0, sizeof p);
+  if (int rc = fill_common(p, plan, dtype, n, ndim, shape, who)) return rc;
+  if (!x_dev || !x_mask || !angle_out_dev) return fail(US_EINVAL, "%s: null pointer table", who);
+  for (int l = 0; l < plan->n_leaves; ++l) {
+    if (!x_dev[l] && n > 0) return fail(US_EINVAL, "%s: leaf %d is null", who, l);
+    p.in[l] = x_dev[l];
+    p.in_mask[l] = x_mask[l];
+  }
+  for (int s = 0; s < plan->n_nodes; ++s) p.out[s] = angle_out_dev[s];
+  p.r_out = r_out_dev;
+  if (n == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = try_launch_from_cartesian_tiled(p, dtype, st);
+  if (rc == 1) return 0;
+  if (rc != 0) return rc;
+  return launch_from_cartesian_strided(p, dtype, st);
+}
+
+// ---- FMA peak probe ----------------------------------------------------------------------
+namespace us {
+template <typename T>
+__global__ void __launch_bounds__(256) fma_probe(T* out, int iters, T a, T b) {
+  T x0 = (T)threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  T s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (s == (T)123456789) out[0] = s;  // never true; keeps the loop alive
+}
+}  // namespace us
+
+extern "C" int us_probe_fma_peak(int dtype, int iters, double* tflops) {
+  if (!tflops || iters < 1) return fail(US_EINVAL, "us_probe_fma_peak: bad arguments");
+  if (dtype != US_F32 && dtype != US_F64) return fail(US_EINVAL, "us_probe_fma_peak: bad dtype");
+  int dev = 0, sms = 0;
+  US_CUDA_TRY(cudaGetDevice(&dev), "cudaGetDevice");
+  US_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute");
+  void* buf = nullptr;
+  US_CUDA_TRY(cudaMalloc(&buf, 64), "cudaMalloc");  // measurement helper only: owns its 64 bytes
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int blocks = sms * 8, threads = 256;
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0, 0);
+    if (dtype == US_F64)
+      fma_probe<double><<<blocks, threads>>>((double*)buf, iters, 0.999999, 1e-9);
+    else
+      fma_probe<float><<<blocks, threads>>>((float*)buf, iters, 0.999999f, 1e-9f);
+    cudaEventRecord(e1, 0);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  US_CUDA_TRY(cudaGetLastError(), "fma_probe");
+  const double flops = 2.0 * 8.0 * (double)iters * (double)blocks * threads;
+  *tflops = flops / ((double)best * 1e-3) / 1e12;
+  return 0;
+}

@@ -1,0 +1,32 @@
+// Kernel-parameter blocks.  They are passed BY VALUE as __grid_constant__ parameters, so the
+// compiled tree, the pointer tables and the broadcast masks all live in the per-launch constant
+// bank: no __constant__ symbol to race on across streams, no H2D copy per call.
+#pragma once
+
+#include "us_common.cuh"
+
+namespace us {
+
+struct XformParams {
+  us_plan_t plan;                   // pre-order program
+  const void* in[US_MAX_LEAVES];    // to: angles (s_nodes order)   from: leaves (c_nodes order)
+  void* out[US_MAX_LEAVES];         // to: leaves (c_nodes order)   from: angles (s_nodes order)
+  const void* r_in;                 // to only; nullptr => r = 1
+  void* r_out;                      // from only; nullptr => not wanted
+  uint32_t in_mask[US_MAX_LEAVES];  // bit d set: input spans launch dim d
+  uint32_t r_mask;
+  int32_t ndim;
+  int64_t n;
+  int64_t shape[US_MAX_DIMS];
+};
+static_assert(sizeof(XformParams) < 32000, "kernel parameter block must fit the 32 KB limit");
+
+int launch_to_cartesian_strided(const XformParams& p, int dtype, cudaStream_t st);
+int launch_from_cartesian_strided(const XformParams& p, int dtype, cudaStream_t st);
+
+// contiguous fast path (us_transform_tma.cu); returns 1 if it took the launch, 0 if the caller
+// should use the strided kernels, <0 / >0 on error
+int try_launch_to_cartesian_tiled(const XformParams& p, int dtype, cudaStream_t st);
+int try_launch_from_cartesian_tiled(const XformParams& p, int dtype, cudaStream_t st);
+
+}  // namespace us

@@ -1,0 +1,300 @@
+// Weighted tensor-product reductions behind integrate()
+// (reference: src/ultrasphere/_integral.py:245-276).
+//
+//   dense     out[m] = sum_grid  prod_i w_i[idx_i] * val[idx..., m]
+//   separable out_a[m] = sum_j w_a[j] * val_a[j, m]          for every axis a in one launch
+//
+// Bound: HBM read of `val` (8 B per quadrature node per trailing element for f64); the 1-D weight
+// tables (<= a few hundred entries per axis) stay in L1.  Accumulation is float64 throughout.
+// Two phases, no atomics: per-block partials (warp shuffle, then a shared-memory tree over the
+// warps) are written to caller-provided scratch and a second, single-block kernel adds them in a
+// fixed order, so the result is bit-reproducible for a given shape.
+#include "us_common.cuh"
+
+namespace us {
+
+constexpr int kRedThreads = 256;
+constexpr int kRedWarps = kRedThreads / 32;
+constexpr int kMaxRedBlocks = 148 * 4;  // one wave at 4 resident CTAs per SM
+constexpr int kSeg = 2048;              // elements of the innermost axis per work item
+
+struct ReduceParams {
+  const void* val;
+  const void* w[US_MAX_DIMS];
+  int64_t extent[US_MAX_DIMS];
+  int32_t ndim;
+  int32_t m;        // trailing elements per node (rows kernel: power of two <= 32)
+  int32_t log2m;
+  int32_t nseg;     // segments per innermost-axis row
+  int64_t rows;     // product of extent[0..ndim-1)
+  int64_t inner;    // extent[ndim-1]
+  int64_t items;    // rows * nseg
+  double* partial;  // [gridDim.x][m]
+};
+
+template <typename T>
+__device__ __forceinline__ double ldw(const void* w, int64_t i) {
+  return (double)__ldg((const T*)w + i);
+}
+
+// A warp walks a contiguous range of (row, segment) work items.  The row's outer weight
+// prod_{i<ndim-1} w_i[idx_i] is warp-uniform; the odometer idx[] is advanced per row instead of
+// re-dividing.  Lanes stride the innermost run of inner*m contiguous values; with m | 32 a lane
+// always lands on the same trailing index, so one accumulator per lane suffices.
+template <typename T>
+__global__ void __launch_bounds__(kRedThreads) wreduce_rows(const __grid_constant__ ReduceParams p) {
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int64_t nwarps = (int64_t)gridDim.x * kRedWarps;
+  const int64_t gw = (int64_t)blockIdx.x * kRedWarps + warp;
+  const int64_t per = (p.items + nwarps - 1) / nwarps;
+  int64_t it = gw * per;
+  const int64_t it_end = min(p.items, it + per);
+  double acc = 0.0;
+  if (it < it_end) {
+    const int nd = p.ndim;
+    int64_t row = it / p.nseg;
+    int seg = (int)(it - row * p.nseg);
+    int64_t idx[US_MAX_DIMS];
+    {
+      int64_t rem = row;
+      for (int d = nd - 2; d >= 0; --d) {
+        const int64_t e = p.extent[d];
+        const int64_t q = rem / e;
+        idx[d] = rem - q * e;
+        rem = q;
+      }
+    }
+    double wrow = 1.0;
+    for (int d = 0; d < nd - 1; ++d) wrow *= ldw<T>(p.w[d], idx[d]);
+    const T* val = (const T*)p.val;
+    const void* wl = p.w[nd - 1];
+    const int64_t run = p.inner << p.log2m;  // contiguous values per row
+    for (; it < it_end; ++it) {
+      const int64_t e0 = (int64_t)seg * kSeg << p.log2m;
+      const int64_t e1 = min(run, e0 + ((int64_t)kSeg << p.log2m));
+      const T* base = val + row * run;
+      double a0 = 0.0, a1 = 0.0;
+      int64_t e = e0 + lane;
+      for (; e + 32 < e1; e += 64) {  // two independent loads in flight per lane
+        const double v0 = (double)ld_stream(base + e);
+        const double v1 = (double)ld_stream(base + e + 32);
+        a0 = fma(ldw<T>(wl, e >> p.log2m), v0, a0);
+        a1 = fma(ldw<T>(wl, (e + 32) >> p.log2m), v1, a1);
+      }
+      if (e < e1) a0 = fma(ldw<T>(wl, e >> p.log2m), (double)ld_stream(base + e), a0);
+      acc = fma(wrow, a0 + a1, acc);
+      if (++seg == p.nseg) {
+        seg = 0;
+        ++row;
+        // odometer carry over the outer axes, then refresh the row weight
+        for (int d = nd - 2; d >= 0; --d) {
+          if (++idx[d] < p.extent[d]) break;
+          idx[d] = 0;
+        }
+        wrow = 1.0;
+        for (int d = 0; d < nd - 1; ++d) wrow *= ldw<T>(p.w[d], idx[d]);
+      }
+    }
+  }
+  // lanes with equal (lane mod m) hold the same trailing index
+  for (int o = 16; o >= p.m; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+  __shared__ double sm[kRedWarps][32];
+  if (lane < p.m) sm[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && lane < p.m) {
+    double t = sm[0][lane];
+#pragma unroll
+    for (int wv = 1; wv < kRedWarps; ++wv) t += sm[wv][lane];
+    p.partial[(int64_t)blockIdx.x * p.m + lane] = t;
+  }
+}
+
+// General trailing size: threads across the trailing index (coalesced), grid.y splits the grid
+// nodes; every node's weight product is recomputed per thread.  Correct for any m; the rows
+// kernel above is the fast path for m in {1,2,4,8,16,32} (real / complex scalars, short vectors).
+template <typename T>
+__global__ void __launch_bounds__(kRedThreads) wreduce_cols(const __grid_constant__ ReduceParams p,
+                                                            int64_t total_nodes, int64_t m64) {
+  const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t per = (total_nodes + gridDim.y - 1) / gridDim.y;
+  const int64_t g0 = (int64_t)blockIdx.y * per;
+  const int64_t g1 = min(total_nodes, g0 + per);
+  if (col >= m64) return;
+  const T* val = (const T*)p.val;
+  double acc = 0.0;
+  for (int64_t g = g0; g < g1; ++g) {
+    int64_t rem = g;
+    double wg = 1.0;
+    for (int d = p.ndim - 1; d >= 0; --d) {
+      const int64_t e = p.extent[d];
+      const int64_t q = rem / e;
+      wg *= ldw<T>(p.w[d], rem - q * e);
+      rem = q;
+    }
+    acc = fma(wg, (double)ld_stream(val + g * m64 + col), acc);
+  }
+  p.partial[(int64_t)blockIdx.y * m64 + col] = acc;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) wreduce_final(const double* __restrict__ partial, int nblocks,
+                                                     int64_t m, T* __restrict__ out, int accumulate) {
+  const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= m) return;
+  double t = 0.0;
+  for (int b = 0; b < nblocks; ++b) t += partial[(int64_t)b * m + col];
+  if (accumulate) t += (double)out[col];
+  out[col] = (T)t;
+}
+
+struct SepParams {
+  const void* w[US_MAX_AXES];
+  const void* val[US_MAX_AXES];
+  void* out[US_MAX_AXES];
+  int64_t len[US_MAX_AXES];
+  int64_t m[US_MAX_AXES];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) separable_reduce(const __grid_constant__ SepParams p) {
+  const int a = blockIdx.x;
+  const int64_t m = p.m[a], len = p.len[a];
+  const T* val = (const T*)p.val[a];
+  const T* w = (const T*)p.w[a];
+  T* out = (T*)p.out[a];
+  if (m == 1) {
+    if (blockIdx.y > 0) return;  // uniform per block
+    // one short dot product: whole block, shuffle + shared tree
+    double acc = 0.0;
+    for (int64_t j = threadIdx.x; j < len; j += blockDim.x) acc = fma((double)w[j], (double)val[j], acc);
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+    __shared__ double sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += sm[k];
+      out[0] = (T)t;
+    }
+    return;
+  }
+  for (int64_t col = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; col < m;
+       col += (int64_t)gridDim.y * blockDim.x) {
+    double acc = 0.0;
+    for (int64_t j = 0; j < len; ++j) acc = fma((double)w[j], (double)val[j * m + col], acc);
+    out[col] = (T)acc;
+  }
+}
+
+static inline bool rows_ok(int64_t m) { return m >= 1 && m <= 32 && (m & (m - 1)) == 0; }
+
+static int reduce_blocks(int64_t m, int64_t total_nodes, int64_t items, int* gx, int* gy) {
+  if (rows_ok(m)) {
+    int64_t b = (items + kRedWarps - 1) / kRedWarps;
+    *gx = (int)(b < 1 ? 1 : (b > kMaxRedBlocks ? kMaxRedBlocks : b));
+    *gy = 1;
+    return *gx;
+  }
+  int64_t cx = (m + kRedThreads - 1) / kRedThreads;
+  int64_t want = kMaxRedBlocks / cx;
+  if (want < 1) want = 1;
+  if (want > total_nodes) want = total_nodes < 1 ? 1 : total_nodes;
+  *gx = (int)cx;
+  *gy = (int)want;
+  return (int)want;
+}
+
+}  // namespace us
+
+using namespace us;
+
+extern "C" int64_t us_weighted_reduce_scratch_bytes(int64_t m) {
+  if (m < 1) return 0;
+  // worst case number of partial rows is kMaxRedBlocks for either kernel
+  return (int64_t)kMaxRedBlocks * m * (int64_t)sizeof(double);
+}
+
+extern "C" int us_weighted_reduce(int dtype, int ndim, const int64_t* extent, const void* const* w_dev,
+                                  const void* val_dev, int64_t m, void* out_dev, int accumulate,
+                                  void* scratch_dev, int64_t scratch_bytes, void* stream) {
+  if (dtype != US_F32 && dtype != US_F64) return fail(US_EINVAL, "us_weighted_reduce: bad dtype %d", dtype);
+  if (ndim < 1 || ndim > US_MAX_DIMS) return fail(US_ECAPACITY, "us_weighted_reduce: ndim %d not in 1..%d", ndim, US_MAX_DIMS);
+  if (!extent || !w_dev || !val_dev || !out_dev || !scratch_dev || m < 1)
+    return fail(US_EINVAL, "us_weighted_reduce: null pointer or m < 1");
+  if (scratch_bytes < us_weighted_reduce_scratch_bytes(m))
+    return fail(US_EINVAL, "us_weighted_reduce: scratch too small (%lld < %lld)", (long long)scratch_bytes,
+                (long long)us_weighted_reduce_scratch_bytes(m));
+  ReduceParams p{};
+  p.val = val_dev;
+  p.ndim = ndim;
+  int64_t total = 1;
+  for (int d = 0; d < ndim; ++d) {
+    if (extent[d] < 1 || !w_dev[d]) return fail(US_EINVAL, "us_weighted_reduce: axis %d empty or null weights", d);
+    p.extent[d] = extent[d];
+    p.w[d] = w_dev[d];
+    total *= extent[d];
+  }
+  p.inner = extent[ndim - 1];
+  p.rows = total / p.inner;
+  p.nseg = (int32_t)((p.inner + kSeg - 1) / kSeg);
+  p.items = p.rows * p.nseg;
+  p.partial = (double*)scratch_dev;
+  cudaStream_t st = (cudaStream_t)stream;
+  int gx, gy;
+  const int nparts = reduce_blocks(m, total, p.items, &gx, &gy);
+  if (rows_ok(m)) {
+    p.m = (int32_t)m;
+    p.log2m = 0;
+    while ((1 << p.log2m) < m) ++p.log2m;
+    if (dtype == US_F32)
+      wreduce_rows<float><<<gx, kRedThreads, 0, st>>>(p);
+    else
+      wreduce_rows<double><<<gx, kRedThreads, 0, st>>>(p);
+  } else {
+    dim3 grid(gx, gy);
+    if (dtype == US_F32)
+      wreduce_cols<float><<<grid, kRedThreads, 0, st>>>(p, total, m);
+    else
+      wreduce_cols<double><<<grid, kRedThreads, 0, st>>>(p, total, m);
+  }
+  US_CUDA_TRY(cudaGetLastError(), "weighted_reduce launch");
+  const int fb = (int)((m + 255) / 256);
+  if (dtype == US_F32)
+    wreduce_final<float><<<fb, 256, 0, st>>>(p.partial, nparts, m, (float*)out_dev, accumulate);
+  else
+    wreduce_final<double><<<fb, 256, 0, st>>>(p.partial, nparts, m, (double*)out_dev, accumulate);
+  US_CUDA_TRY(cudaGetLastError(), "weighted_reduce final launch");
+  return 0;
+}
+
+extern "C" int us_separable_reduce(int dtype, int n_axes, const int64_t* len, const int64_t* m,
+                                   const void* const* w_dev, const void* const* val_dev,
+                                   void* const* out_dev, void* stream) {
+  if (dtype != US_F32 && dtype != US_F64) return fail(US_EINVAL, "us_separable_reduce: bad dtype %d", dtype);
+  if (n_axes < 1 || n_axes > US_MAX_AXES)
+    return fail(US_ECAPACITY, "us_separable_reduce: n_axes %d not in 1..%d", n_axes, US_MAX_AXES);
+  if (!len || !m || !w_dev || !val_dev || !out_dev) return fail(US_EINVAL, "us_separable_reduce: null table");
+  SepParams p{};
+  int64_t mmax = 1;
+  for (int a = 0; a < n_axes; ++a) {
+    if (len[a] < 1 || m[a] < 1 || !w_dev[a] || !val_dev[a] || !out_dev[a])
+      return fail(US_EINVAL, "us_separable_reduce: axis %d has an empty extent or a null pointer", a);
+    p.len[a] = len[a];
+    p.m[a] = m[a];
+    p.w[a] = w_dev[a];
+    p.val[a] = val_dev[a];
+    p.out[a] = out_dev[a];
+    if (m[a] > mmax) mmax = m[a];
+  }
+  int64_t gy = (mmax + 255) / 256;
+  if (gy > 1024) gy = 1024;
+  dim3 grid(n_axes, (unsigned)gy);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == US_F32)
+    separable_reduce<float><<<grid, 256, 0, st>>>(p);
+  else
+    separable_reduce<double><<<grid, 256, 0, st>>>(p);
+  US_CUDA_TRY(cudaGetLastError(), "separable_reduce launch");
+  return 0;
+}

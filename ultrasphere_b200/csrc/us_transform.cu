@@ -1,0 +1,172 @@
+// Cartesian <-> polyspherical transforms: strided/broadcast kernels ("generic path").
+//
+// One thread owns one point and interprets the compiled pre-order program (us_plan) that sits
+// in the kernel-parameter constant bank.  All control flow depends only on the program, so it
+// is warp-uniform; the only per-thread state is the running product / norm and the small
+// deferred-branch stack.  Inputs may be broadcast along any launch dimension (mask bits), which
+// is what integrands inside integrate() pass: s_ndim one-dimensional axes of a tensor grid.
+//
+// Reference semantics: src/ultrasphere/_coordinates.py:555-579 (from) and :636-656 (to).
+#include "us_common.cuh"
+#include "us_params.cuh"
+
+namespace us {
+
+// Decompose a linear index over shape[0..ndim) once per thread; offsets of broadcast inputs are
+// then a short dot product with the dense strides of the dims their mask selects.
+struct Indexer {
+  int64_t lin;
+  int ndim;
+  uint32_t full;
+  int64_t idx[US_MAX_DIMS];
+  const int64_t* shape;
+
+  __device__ __forceinline__ Indexer(const XformParams& p, int64_t i)
+      : lin(i), ndim(p.ndim), full(p.ndim >= 32 ? 0xFFFFFFFFu : ((1u << p.ndim) - 1u)), shape(p.shape) {
+    if (ndim > 1) {
+      int64_t rem = i;
+      for (int d = ndim - 1; d >= 0; --d) {
+        int64_t e = shape[d];
+        int64_t qd = rem / e;
+        idx[d] = rem - qd * e;
+        rem = qd;
+      }
+    }
+  }
+  __device__ __forceinline__ int64_t off(uint32_t mask) const {
+    if (mask == full) return lin;
+    if (mask == 0u) return 0;
+    int64_t o = 0, mul = 1;
+    for (int d = ndim - 1; d >= 0; --d) {
+      if ((mask >> d) & 1u) {
+        o += idx[d] * mul;
+        mul *= shape[d];
+      }
+    }
+    return o;
+  }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) to_cartesian_strided(const __grid_constant__ XformParams p) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n) return;
+  Indexer ix(p, i);
+  T cur = p.r_in ? ld_stream((const T*)p.r_in + ix.off(p.r_mask)) : T(1);
+  T stack[US_MAX_STACK];
+  int sp = 0;
+  const int nn = p.plan.n_nodes;
+  for (int k = 0; k < nn; ++k) {
+    const uint64_t w = p.plan.node[k];
+    const int slot = node_slot(w);
+    const T th = ld_stream((const T*)p.in[slot] + ix.off(p.in_mask[slot]));
+    T s, c;
+    sincos_t(th, &s, &c);
+    const T pc = mul_rn(cur, c);
+    const T ps = mul_rn(cur, s);
+    T* oc = nullptr;
+    T* os = nullptr;
+    switch (node_kind(w)) {
+      case US_NODE_A:
+        oc = (T*)p.out[node_cos_leaf(w)];
+        os = (T*)p.out[node_sin_leaf(w)];
+        if (sp > 0) cur = stack[--sp];
+        break;
+      case US_NODE_B:
+        oc = (T*)p.out[node_cos_leaf(w)];
+        cur = ps;
+        break;
+      case US_NODE_BP:
+        os = (T*)p.out[node_sin_leaf(w)];
+        cur = pc;
+        break;
+      default:  // US_NODE_C: defer the sin branch, descend into the cos branch
+        stack[sp++] = ps;
+        cur = pc;
+        break;
+    }
+    if (oc) st_stream(oc + i, pc);
+    if (os) st_stream(os + i, ps);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) from_cartesian_strided(const __grid_constant__ XformParams p) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n) return;
+  Indexer ix(p, i);
+  const int nn = p.plan.n_nodes;
+  // r: leaves in c_nodes order, sequential, every square and add rounded once.
+  if (p.r_out) {
+    T acc = T(0);
+    for (int l = 0; l < p.plan.n_leaves; ++l) {
+      const T x = __ldg((const T*)p.in[l] + ix.off(p.in_mask[l]));
+      const T sq = mul_rn(x, x);
+      acc = (l == 0) ? sq : add_rn(acc, sq);
+    }
+    st_stream((T*)p.r_out + i, sqrt_rn(acc));
+  }
+  // children before parents = the pre-order program walked backwards
+  T stack[US_MAX_STACK];
+  int sp = 0;
+  T cur = T(0);
+  for (int k = nn - 1; k >= 0; --k) {
+    const uint64_t w = p.plan.node[k];
+    T vc, vs;
+    switch (node_kind(w)) {
+      case US_NODE_A: {
+        if (k != nn - 1) stack[sp++] = cur;  // a finished sibling subtree waits for its `c` parent
+        const int lc = node_cos_leaf(w), ls = node_sin_leaf(w);
+        vc = __ldg((const T*)p.in[lc] + ix.off(p.in_mask[lc]));
+        vs = __ldg((const T*)p.in[ls] + ix.off(p.in_mask[ls]));
+        break;
+      }
+      case US_NODE_B: {
+        const int lc = node_cos_leaf(w);
+        vc = __ldg((const T*)p.in[lc] + ix.off(p.in_mask[lc]));
+        vs = cur;
+        break;
+      }
+      case US_NODE_BP: {
+        const int ls = node_sin_leaf(w);
+        vs = __ldg((const T*)p.in[ls] + ix.off(p.in_mask[ls]));
+        vc = cur;
+        break;
+      }
+      default:
+        vc = cur;
+        vs = stack[--sp];
+        break;
+    }
+    T* o = (T*)p.out[node_slot(w)];
+    if (o) st_stream(o + i, atan2_t(vs, vc));
+    // numpy: vector_norm(stack((sin, cos))) = sqrt(sin*sin + cos*cos), squares rounded first
+    cur = sqrt_rn(add_rn(mul_rn(vs, vs), mul_rn(vc, vc)));
+  }
+}
+
+int launch_to_cartesian_strided(const XformParams& p, int dtype, cudaStream_t st) {
+  const int threads = 256;
+  const int64_t blocks = (p.n + threads - 1) / threads;
+  if (blocks > 0x7FFFFFFFLL) return fail(US_EINVAL, "us_to_cartesian: n too large for one launch");
+  if (dtype == US_F32)
+    to_cartesian_strided<float><<<(unsigned)blocks, threads, 0, st>>>(p);
+  else
+    to_cartesian_strided<double><<<(unsigned)blocks, threads, 0, st>>>(p);
+  US_CUDA_TRY(cudaGetLastError(), "to_cartesian_strided launch");
+  return 0;
+}
+
+int launch_from_cartesian_strided(const XformParams& p, int dtype, cudaStream_t st) {
+  const int threads = 256;
+  const int64_t blocks = (p.n + threads - 1) / threads;
+  if (blocks > 0x7FFFFFFFLL) return fail(US_EINVAL, "us_from_cartesian: n too large for one launch");
+  if (dtype == US_F32)
+    from_cartesian_strided<float><<<(unsigned)blocks, threads, 0, st>>>(p);
+  else
+    from_cartesian_strided<double><<<(unsigned)blocks, threads, 0, st>>>(p);
+  US_CUDA_TRY(cudaGetLastError(), "from_cartesian_strided launch");
+  return 0;
+}
+
+}  // namespace us
