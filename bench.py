@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: create_standard(9) (10-D `bbbbbbbba`) float32 round trip
+(from_cartesian → to_cartesian), BASELINE.json configs[1].
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One process per GPU (torchrun for N>1).  A step is one round trip over one batch of
+POINTS_PER_GPU synthetic points resident in HBM.  Rank 0 prints ONE JSON line.
+
+  value      whole-job round-trip points/s, inputs resident in HBM, CUDA-event timed, max over ranks
+  roofline   the dominant kernel's algorithmic HBM bytes / its event-timed duration / measured peak
+  e2e        the same round trip through the public API from pinned HOST buffers, copies included
+  cpu_baseline  the NumPy oracle (port of the reference's path) on this box's host, bounded sample
+
+``--impl reference`` times the reference's own CPU algorithm (the NumPy port in ``oracle/``; the
+reference is pure Python and cannot travel to the GPU box) on all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+S_NDIM = 9
+C_NDIM = 10
+POINTS_PER_GPU = 256_000_000
+E2E_POINTS = 32_000_000
+E2E_CHUNK = 4_000_000
+CPU_SAMPLE = 1 << 23
+METRIC = "round-trip points/s (create_standard(9) float32: from_cartesian then to_cartesian)"
+UNIT = "points/s"
+BYTES_PER_POINT_ONE_WAY = 2 * C_NDIM * 4  # (n_in + n_out) * sizeof(float32)
+
+
+def parse() -> argparse.Namespace:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--points", type=int, default=POINTS_PER_GPU, help="points per GPU (default: the BASELINE size)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = (
+        "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+        "clocks_event_reasons.sw_power_cap"
+    )
+
+    def __init__(self, index: int) -> None:
+        self.rows: list[list[str]] = []
+        self.proc: subprocess.Popen | None = None
+        self.index = index
+
+    def start(self) -> None:
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )
+        except OSError:
+            self.proc = None
+            return
+
+        def pump() -> None:
+            assert self.proc is not None and self.proc.stdout is not None
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for row in self.rows:
+            if len(row) < 7:
+                continue
+            try:
+                sm.append(float(row[0]))
+                mx.append(float(row[1]))
+                pw.append(float(row[2]))
+            except ValueError:
+                continue
+            for name, cell in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), row[3:7]):
+                if cell.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # "under load": samples drawing more than half of the peak power seen
+        hot = [s for s, p in zip(sm, pw) if p >= 0.5 * max(pw)] or sm
+        hot.sort()
+        return {"sm_mhz": hot[len(hot) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU legs (oracle port)
+# ----------------------------------------------------------------------------------------------
+def cpu_round_trip(tree, x) -> None:
+    from oracle import vks_oracle as vo
+
+    sph = vo.from_cartesian(tree, x)
+    vo.to_cartesian(tree, sph, as_array=True)
+
+
+def cpu_baseline_single_core(sample: int) -> dict:
+    import numpy as np
+
+    from oracle import vks_oracle as vo
+
+    tree = vo.create_standard(S_NDIM)
+    x = np.random.default_rng(0).uniform(-1, 1, (C_NDIM, sample)).astype(np.float32)
+    cpu_round_trip(tree, x[:, : sample // 8])
+    best = float("inf")
+    for _ in range(2):
+        t0 = time.perf_counter()
+        cpu_round_trip(tree, x)
+        best = min(best, time.perf_counter() - t0)
+    return {
+        "value": sample / best,
+        "unit": UNIT,
+        "cores": 1,
+        "kind": "port",
+        "sample": f"{sample} points of the same workload, best of 2, NumPy ufuncs are single-threaded (host has {os.cpu_count()} cpus)",
+    }
+
+
+def run_reference(args: argparse.Namespace) -> None:
+    """The reference's CPU algorithm (NumPy port) on every host core: the batch is cut into one
+    slice per thread (NumPy releases the GIL inside ufuncs)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from concurrent.futures import ThreadPoolExecutor
+
+    import numpy as np
+
+    from oracle import vks_oracle as vo
+
+    cores = os.cpu_count() or 1
+    tree = vo.create_standard(S_NDIM)
+    sample = min(args.points, CPU_SAMPLE)
+    x = np.random.default_rng(0).uniform(-1, 1, (C_NDIM, sample)).astype(np.float32)
+    bounds = np.linspace(0, sample, cores + 1).astype(int)
+    parts = [np.ascontiguousarray(x[:, lo:hi]) for lo, hi in zip(bounds[:-1], bounds[1:]) if hi > lo]
+    with ThreadPoolExecutor(max_workers=cores) as pool:
+        def step() -> None:
+            list(pool.map(lambda part: cpu_round_trip(tree, part), parts))
+
+        for _ in range(args.warmup):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+        dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    desc = f"{sample} points per step split over {len(parts)} threads"
+    print(json.dumps({
+        "impl": "reference",
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "create_standard(9) bbbbbbbba float32 round trip", "points_per_step": sample,
+                   "runs_on": "host CPU (NumPy port of the reference's path; the Python reference cannot travel to the GPU box)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ----------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------
+def run_b200(args: argparse.Namespace) -> None:
+    import torch
+    import torch.distributed as dist
+
+    import ultrasphere_b200 as us
+    from ultrasphere_b200._host import HostPipeline
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.points
+    c = us.create_standard(S_NDIM)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x = torch.rand((C_NDIM, n), device=dev, dtype=torch.float32, generator=gen).mul_(2).sub_(1)
+
+    def barrier() -> None:
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sph = None
+    for _ in range(max(args.warmup, 3)):
+        sph = c.from_cartesian(x)
+        back = c.to_cartesian(sph, as_array=True)
+    # parity spot check inside the bench run: the round trip must reproduce the input
+    err = ((back[:, : 1 << 20] - x[:, : 1 << 20]).abs().amax(0) / sph["r"][: 1 << 20]).max().item()
+    if not err <= 8 * 1.1920929e-07:
+        raise SystemExit(f"bench.py: round-trip error {err} exceeds 8 eps — refusing to report a number")
+    del back
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    t_begin = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_begin.record()
+    for k in range(args.steps):
+        ev[k][0].record()
+        sph = c.from_cartesian(x)
+        ev[k][1].record()
+        back = c.to_cartesian(sph, as_array=True)
+        ev[k][2].record()
+    t_end.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = t_begin.elapsed_time(t_end)
+    from_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
+    to_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
+    stats = torch.tensor([total_ms, from_ms, to_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    total_ms, from_ms, to_ms = (float(v) for v in stats.tolist())
+    value = world * n * args.steps / (total_ms * 1e-3)
+    del back, sph
+
+    # ---- end to end from host buffers (per rank, same tree, E2E_POINTS points) -----------------
+    e2e = None
+    if not args.no_e2e:
+        ne = min(E2E_POINTS, n)
+        del x
+        torch.cuda.empty_cache()
+        hx = {k: torch.empty(ne, dtype=torch.float32).uniform_(-1, 1).pin_memory() for k in c.c_nodes}
+        hs = {k: torch.empty(ne, dtype=torch.float32).pin_memory() for k in ["r"] + list(c.s_nodes)}
+        hb = {k: torch.empty(ne, dtype=torch.float32).pin_memory() for k in c.c_nodes}
+        pipe = HostPipeline(c, device=dev, chunk_points=E2E_CHUNK)
+        for _ in range(2):
+            pipe.round_trip(hx, hs, hb)
+        esteps = max(3, min(args.steps, 10))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(esteps):
+            pipe.round_trip(hx, hs, hb)
+        barrier()
+        dt = time.perf_counter() - t0
+        worst = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+        dt = float(worst.item())
+        bad = max((hb[k][:100000] - hx[k][:100000]).abs().max().item() for k in c.c_nodes)
+        if not bad <= 4e-6:
+            raise SystemExit(f"bench.py: e2e round-trip error {bad}")
+        e2e = {
+            "value": world * ne * esteps / dt,
+            "unit": UNIT,
+            "h2d_bytes_per_step": pipe.bytes_h2d,
+            "d2h_bytes_per_step": pipe.bytes_d2h,
+            "points_per_step_per_gpu": ne,
+            "steps": esteps,
+            "launches_per_step": pipe.launches,
+            "how": "pinned host dict-of-arrays -> HostPipeline.round_trip (chunked H2D / from_cartesian / to_cartesian / D2H of spherical and Cartesian results on 3 streams), wall clock around the calls, max over ranks",
+        }
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(peaks_path):
+        with open(peaks_path) as fh:
+            peak, peak_src = float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    dom, dom_ms = ("us::from_cartesian", from_ms) if from_ms >= to_ms else ("us::to_cartesian", to_ms)
+    alg_bytes = BYTES_PER_POINT_ONE_WAY * n
+    achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(tpath):
+        with open(tpath) as fh:
+            traffic = json.load(fh).get(dom)
+    roofline = {
+        "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+        "ms_per_launch": dom_ms,
+        "other_kernel": {"from_cartesian_ms": from_ms, "to_cartesian_ms": to_ms,
+                         "from_cartesian_gbs": alg_bytes / (from_ms * 1e-3) / 1e9, "to_cartesian_gbs": alg_bytes / (to_ms * 1e-3) / 1e9},
+    }
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": "create_standard(9) bbbbbbbba float32 round trip (BASELINE.json configs[1])",
+            "points_per_gpu": n, "global_points": world * n, "parallelism": f"batch sharded over {world} GPU(s), no collective",
+            "l2": "inputs (10.24 GB per array set) exceed the 126 MB L2; no flush needed",
+            "inputs": "U(-1,1) per leaf, torch.Generator(cuda).manual_seed(1234+rank), resident in HBM",
+        },
+        "roofline": roofline, "e2e": e2e, "gpu_launches": 2 * args.steps, "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_single_core(min(CPU_SAMPLE, n))
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,209 @@
+"""integrate() / roots() on the CUDA path against the oracle and the reference's golden values."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import ultrasphere_b200 as us
+from oracle import vks_oracle as vo
+from tests.helpers import GOLDEN, INTEGRAL_REL, make
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+QD = np.load(os.path.join(GOLDEN, "quadrature.npz"))
+QUAD_SPECS = sorted({k.split("|")[0] for k in QD.files})
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("spec", QUAD_SPECS)
+def test_roots_are_the_reference_tables(spec):
+    c = make(us, spec)
+    for n in (4, 7, 12):
+        xs, ws = us.roots(c, n, expand_dims_x=False, xp=torch, device=DEV, dtype=torch.float64)
+        for i, node in enumerate(c.s_nodes):
+            np.testing.assert_allclose(host(xs[node]), QD[f"{spec}|n{n}|x{i}"], rtol=1e-14, atol=1e-15)
+            np.testing.assert_allclose(host(ws[node]), QD[f"{spec}|n{n}|w{i}"], rtol=1e-13, atol=1e-300)
+        xe, we = us.roots(c, n, expand_dims_x=True, expand_dims_w=True, xp=torch, device=DEV, dtype=torch.float64)
+        for i, node in enumerate(c.s_nodes):
+            shp = [1] * c.s_ndim
+            shp[i] = xs[node].numel()
+            assert list(xe[node].shape) == shp and list(we[node].shape) == shp
+
+
+def test_roots_dtype_quirk_matches_reference():
+    """dtype=None: type-a angles come from arange (default dtype), the others from float64 tables."""
+    c = us.create_spherical()
+    xs, ws = us.roots(c, 5, expand_dims_x=False, xp=torch, device=DEV)
+    assert xs["theta"].dtype == torch.float64 and xs["phi"].dtype == torch.get_default_dtype()
+
+
+@pytest.mark.parametrize("slab", [None, 0, 4096])
+@pytest.mark.parametrize("spec", QUAD_SPECS)
+def test_integrals_match_reference_golden(spec, slab):
+    c = make(us, spec)
+    k = torch.from_numpy(QD[f"{spec}|k"]).to(DEV)
+
+    def f(s):
+        return torch.exp(torch.einsum("v,v...->...", k, c.to_cartesian(s, as_array=True)))
+
+    def fv(s):
+        x = c.to_cartesian(s, as_array=True)
+        ph = torch.einsum("v,v...->...", k, x)
+        return torch.stack([torch.exp(1j * ph), ph**2 + 0j, torch.exp(ph) + 1j * x[0]], dim=-1)
+
+    def fsep(s):
+        return {
+            node: torch.stack([torch.cos(s[node]) ** 2, 1.0 + 0 * s[node], torch.sin(s[node])], dim=-1)
+            for node in c.s_nodes
+        }
+
+    kw = dict(xp=torch, device=DEV, dtype=torch.float64)
+    for n in (4, 7, 12):
+        if f"{spec}|n{n}|dense" not in QD.files:
+            continue
+        want = QD[f"{spec}|n{n}|dense"]
+        got = us.integrate(c, f, False, n, slab_bytes=slab, **kw)
+        assert got.shape == () and got.dtype == torch.float64
+        assert abs(got.item() - float(want)) <= INTEGRAL_REL * abs(float(want)), (spec, n)
+        wantv = QD[f"{spec}|n{n}|dense_vec"]
+        gotv = host(us.integrate(c, fv, False, n, slab_bytes=slab, **kw))
+        assert gotv.shape == wantv.shape and gotv.dtype == np.complex128
+        scale = np.abs(wantv).max()
+        assert np.abs(gotv - wantv).max() <= INTEGRAL_REL * max(scale, 1.0) * 10, (spec, n)
+        sep = us.integrate(c, fsep, True, n, **kw)
+        assert list(sep) == list(c.s_nodes)
+        gots = np.stack([host(sep[node]) for node in c.s_nodes])
+        np.testing.assert_allclose(gots, QD[f"{spec}|n{n}|sep"], rtol=INTEGRAL_REL, atol=1e-13)
+
+
+def test_analytic_and_doctest_known_answers():
+    with open(os.path.join(GOLDEN, "kat.json")) as fh:
+        kat = json.load(fh)
+    c = us.create_spherical()
+    val = us.integrate(c, lambda s: s["theta"] ** 2 * s["phi"], False, 10, xp=torch, device=DEV, dtype=torch.float64)
+    assert round(val.item(), 5) == kat["integrate_theta2_phi_n10_rounded"]
+    want = float.fromhex(kat["integrate_theta2_phi_n10"])
+    assert abs(val.item() - want) <= INTEGRAL_REL * abs(want)
+    k5 = np.asarray([float.fromhex(h) for h in kat["exp_kx_std4_k"]])
+    kd = torch.from_numpy(k5).to(DEV)
+    c4 = us.create_standard(4)
+    f = lambda s: torch.exp(torch.einsum("v,v...->...", kd, c4.to_cartesian(s, as_array=True)))  # noqa: E731
+    for n, key in ((16, "exp_kx_std4_n16"), (24, "exp_kx_std4_n24")):
+        got = us.integrate(c4, f, False, n, xp=torch, device=DEV, dtype=torch.float64).item()
+        assert abs(got - float.fromhex(kat[key])) <= INTEGRAL_REL * abs(got)
+        assert abs(got - vo.analytic_exp_kx(k5)) <= INTEGRAL_REL * abs(got)
+
+
+# ---- the reference's own tests (tests/test_integral.py) on the CUDA path ---------------------
+@pytest.mark.parametrize("n", [4, 8, 16])
+@pytest.mark.parametrize("value, expected", [(1, 4 * math.pi), (1j, 4j * math.pi)])
+def test_sphere_surface_integrate(value, expected, n):
+    def f2(s):
+        return torch.asarray(value, device=DEV) * torch.ones_like(s["theta"], device=DEV)
+
+    got = us.integrate(us.create_spherical(), f2, does_f_support_separation_of_variables=False, n=n, xp=torch, device=DEV)
+    assert got.item() == pytest.approx(expected, rel=1e-2)
+
+
+@pytest.mark.parametrize("r", [1, 3])
+@pytest.mark.parametrize("n", [4, 8, 16])
+@pytest.mark.parametrize("factory", [us.create_spherical, lambda: us.create_standard(3), lambda: us.create_hopf(2)])
+@pytest.mark.parametrize("concat", [True, False])
+def test_integrate_surface_area(factory, n, concat, r):
+    c = factory()
+
+    def f(s):
+        if concat:
+            return torch.asarray(r**c.s_ndim) * torch.ones_like(next(iter(s.values())))
+        return {k: torch.asarray(r, device=DEV) * torch.ones_like(s[k], device=DEV) for k in c.s_nodes}
+
+    actual = us.integrate(c, f, does_f_support_separation_of_variables=not concat, n=n, xp=torch, device=DEV)
+    if not concat:
+        actual = torch.prod(torch.stack(list(actual.values())))
+    assert actual.item() == pytest.approx(c.surface_area(r), rel=1e-2)
+
+
+@pytest.mark.parametrize("n", [3, 4, 5])
+def test_integrate_match_across_trees(n):
+    cs = [us.create_random(n - 1) for _ in range(4)]
+    k = torch.rand((n,), device=DEV)
+
+    def create_f(c):
+        def f(s):
+            x = c.to_cartesian(s, as_array=True)
+            return torch.einsum("v,v...->...", k.to(x.dtype), x)
+
+        return f
+
+    actual = [us.integrate(c, create_f(c), does_f_support_separation_of_variables=False, n=8, xp=torch, device=DEV) for c in cs]
+    assert torch.allclose(torch.stack(actual), actual[0], rtol=1e-3, atol=1e-3)
+
+
+def test_surface_area_to_machine_precision():
+    for c in (us.create_standard(4), us.create_hopf(3), us.create_standard_prime(4), us.create_random(6, rng=np.random.default_rng(1))):
+        got = us.integrate(c, lambda s: torch.ones((1,) * c.s_ndim, device=DEV, dtype=torch.float64), False, 10, xp=torch, device=DEV, dtype=torch.float64)
+        assert abs(got.item() - c.surface_area()) <= 1e-13 * c.surface_area()
+
+
+def test_integrand_given_as_values_and_errors():
+    c = us.create_standard(3)
+    xs, ws = us.roots(c, 6, expand_dims_x=True, xp=torch, device=DEV, dtype=torch.float64)
+    vals = torch.cos(xs["theta0"]) ** 2 * torch.sin(xs["theta1"]) ** 2 + 0 * xs["theta2"]
+    a = us.integrate(c, vals, False, 6, xp=torch, device=DEV, dtype=torch.float64)
+    b = us.integrate(c, lambda s: torch.cos(s["theta0"]) ** 2 * torch.sin(s["theta1"]) ** 2 + 0 * s["theta2"], False, 6, xp=torch, device=DEV, dtype=torch.float64)
+    assert abs(a.item() - b.item()) <= 1e-14 * abs(a.item())
+    with pytest.raises(ValueError):
+        us.integrate(c, lambda s: torch.ones(3, device=DEV), False, 6, xp=torch, device=DEV)
+    # float32 integrand
+    got32 = us.integrate(c, lambda s: torch.cos(s["theta0"]) ** 2 + 0 * s["theta1"] + 0 * s["theta2"], False, 8, xp=torch, device=DEV, dtype=torch.float32)
+    assert got32.dtype == torch.float32
+    t = vo.create_standard(3)
+    want = vo.integrate(t, lambda s: np.cos(s["theta0"]) ** 2 + 0 * s["theta1"] + 0 * s["theta2"], False, 8)
+    assert abs(got32.item() - float(want)) <= 1e-5 * abs(float(want))
+
+
+@pytest.mark.parametrize("m", [1, 2, 3, 5, 8, 32, 33, 100, 700])
+def test_weighted_reduce_trailing_sizes(m):
+    """Both reduction kernels (rows: m | 32, columns: any m) against float64 NumPy."""
+    rng = np.random.default_rng(m)
+    ext = (5, 7, 12)
+    val = rng.normal(size=ext + (m,))
+    ws = [rng.uniform(0.1, 1, e) for e in ext]
+    want = np.einsum("i,j,k,ijkm->m", *ws, val)
+    got = host(us.weighted_reduce(torch.from_numpy(val).to(DEV), [torch.from_numpy(w).to(DEV) for w in ws]))
+    scale = np.einsum("i,j,k,ijkm->m", *ws, np.abs(val))
+    assert np.all(np.abs(got - want) <= 1e-13 * scale)
+    acc = torch.from_numpy(want.copy()).to(DEV)
+    us.weighted_reduce(torch.from_numpy(val).to(DEV), [torch.from_numpy(w).to(DEV) for w in ws], out=acc)
+    assert np.all(np.abs(host(acc) - 2 * want) <= 2e-13 * scale)
+
+
+def test_weighted_reduce_long_inner_axis_and_single_axis():
+    rng = np.random.default_rng(0)
+    val = rng.normal(size=(3, 10000))
+    ws = [rng.uniform(0.1, 1, 3), rng.uniform(0.1, 1, 10000)]
+    want = np.einsum("i,j,ij->", *ws, val)
+    got = us.weighted_reduce(torch.from_numpy(val).to(DEV), [torch.from_numpy(w).to(DEV) for w in ws]).item()
+    assert abs(got - want) <= 1e-12 * np.einsum("i,j,ij->", *ws, np.abs(val))
+    v1 = rng.normal(size=(100001,))
+    w1 = rng.uniform(0, 1, 100001)
+    got = us.weighted_reduce(torch.from_numpy(v1).to(DEV), [torch.from_numpy(w1).to(DEV)]).item()
+    assert abs(got - float(w1 @ v1)) <= 1e-12 * float(w1 @ np.abs(v1))
+
+
+def test_full_size_quadrature_matches_analytic():
+    """BASELINE config 5: create_standard(4), n=96 (169,869,312 nodes), f = exp(k.x), float64."""
+    k5 = np.random.default_rng(0).uniform(0, 1, 5)
+    kd = torch.from_numpy(k5).to(DEV)
+    c = us.create_standard(4)
+    f = lambda s: torch.exp(torch.einsum("v,v...->...", kd, c.to_cartesian(s, as_array=True)))  # noqa: E731
+    got = us.integrate(c, f, False, 96, xp=torch, device=DEV, dtype=torch.float64).item()
+    want = vo.analytic_exp_kx(k5)
+    assert abs(got - want) <= INTEGRAL_REL * want
+    assert abs(got - 29.44939782558211) <= INTEGRAL_REL * want  # the reference's own n=96 value

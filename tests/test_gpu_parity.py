@@ -1,0 +1,373 @@
+"""Parity of the CUDA path (through the public API → C ABI) with the NumPy oracle and with the
+golden vectors of the unmodified reference.  Needs a B200: run with ``-m gpu``.
+
+Tolerances (see tests/helpers.py and DESIGN.md "Tolerances"):
+  float64  r bit-identical; angles <= 4 ulp; leaves |dx| <= 4 ulp(r)  [r = norm of the point]
+           and element-wise <= 4 + 2*depth ulp (every ancestor contributes one sin/cos whose
+           last-bit rounding differs between libdevice and NumPy's SIMD kernels)
+  float32  r bit-identical; angles and leaves <= 2e-6 relative element-wise (floor: 2e-6 * r
+           absolute for leaves that are exact zeros of sin/cos)
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import ultrasphere_b200 as us
+from oracle import vks_oracle as vo
+from tests.helpers import F32_REL, F64_ULP, GOLDEN, make
+from ultrasphere_b200._plan import plan_for
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+SPECS = [
+    "polar", "spherical", "standard:1", "standard:2", "standard:4", "standard:9", "standard:40",
+    "standard_prime:3", "standard_prime:8", "hopf:1", "hopf:2", "hopf:3", "hopf:5",
+    "random:1:0", "random:5:0", "random:6:3", "random:32:0", "random:32:1", "random:103:7",
+    "expr:cbaa", "expr:cbbaa", "expr:cbabba", "expr:cab'a", "expr:bpbpa",
+]
+DTYPES = [("f32", np.float32, torch.float32), ("f64", np.float64, torch.float64)]
+
+
+def dev(a: np.ndarray) -> torch.Tensor:
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def host(t: torch.Tensor) -> np.ndarray:
+    return t.detach().cpu().numpy()
+
+
+def depth_of(c) -> np.ndarray:
+    ct = plan_for(c)
+    return np.asarray([len(a) for a in ct.leaf_ancestors])
+
+
+def assert_angles_close(got: np.ndarray, want: np.ndarray, what=""):
+    assert got.dtype == want.dtype and got.shape == want.shape
+    if got.dtype == np.float64:
+        d = vo.ulp_distance(got, want)
+        assert d.max() <= F64_ULP, f"{what}: {d.max()} ulp"
+    else:
+        err = np.abs(got.astype(np.float64) - want.astype(np.float64))
+        assert (err <= F32_REL * np.abs(want.astype(np.float64))).all(), f"{what}: rel {np.max(err / np.abs(want))}"
+
+
+def assert_leaves_close(got: np.ndarray, want: np.ndarray, r: np.ndarray, depth: np.ndarray, what=""):
+    """got/want: (c_ndim, *shape); r broadcastable to shape; depth: (c_ndim,)."""
+    assert got.dtype == want.dtype and got.shape == want.shape
+    g, w = got.astype(np.float64), want.astype(np.float64)
+    err = np.abs(g - w)
+    rr = np.abs(np.broadcast_to(r, got.shape[1:]).astype(np.float64))[None]
+    if got.dtype == np.float64:
+        assert (err <= F64_ULP * np.spacing(rr)).all(), f"{what}: {np.max(err / np.spacing(rr))} ulp(r)"
+        d = vo.ulp_distance(got, want)
+        lim = (F64_ULP + 2 * depth).reshape((-1,) + (1,) * (got.ndim - 1))
+        assert (d <= lim).all(), f"{what}: {d.max()} ulp element-wise"
+    else:
+        ok = (err <= F32_REL * np.abs(w)) | (err <= F32_REL * np.finfo(np.float32).eps * rr)
+        assert ok.all(), f"{what}: rel {np.nanmax(err / np.abs(w))}"
+
+
+@pytest.mark.parametrize("dname,ndt,tdt", DTYPES)
+@pytest.mark.parametrize("spec", SPECS)
+def test_transforms_match_oracle(spec, dname, ndt, tdt):
+    c, t = make(us, spec), vo.make(spec)
+    n = 20000 if c.s_ndim <= 40 else 3000
+    x = np.random.default_rng(11).uniform(-1, 1, (c.c_ndim, n)).astype(ndt)
+    want = vo.from_cartesian(t, x)
+    got = c.from_cartesian(dev(x))  # array input, indexed by leaf id
+    assert list(got) == list(want) == ["r"] + list(reversed(c.s_nodes))
+    assert all(v.dtype == tdt and v.shape == (n,) for v in got.values())
+    assert np.array_equal(host(got["r"]), want["r"]), "r must be bit-identical"
+    for k in c.s_nodes:
+        assert_angles_close(host(got[k]), want[k], f"{spec} {k}")
+    # to_cartesian fed with the ORACLE's angles: isolates this kernel's error
+    sph = {k: dev(v) for k, v in want.items()}
+    back = c.to_cartesian(sph)
+    wantx = vo.to_cartesian(t, want)
+    assert list(back) == list(wantx) == list(c.c_nodes)
+    assert_leaves_close(
+        np.stack([host(back[k]) for k in c.c_nodes]), np.stack([wantx[k] for k in c.c_nodes]), want["r"], depth_of(c), spec
+    )
+    # mapping input gives the same bits as array input; as_array stacks the same bits
+    got2 = c.from_cartesian({k: dev(x[i]) for i, k in enumerate(c.c_nodes)})
+    for k in got:
+        assert torch.equal(got[k], got2[k])
+    arr = c.to_cartesian(sph, as_array=True)
+    assert arr.shape == (c.c_ndim, n) and all(torch.equal(arr[i], back[k]) for i, k in enumerate(c.c_nodes))
+    # GPU round trip against the input
+    rt = host(c.to_cartesian(got, as_array=True)).astype(np.float64)
+    tol = 8 * np.finfo(ndt).eps
+    assert np.max(np.abs(rt - x) / want["r"][None]) <= tol
+
+
+TR = np.load(os.path.join(GOLDEN, "transforms.npz"))
+GOLDEN_SPECS = sorted({k.split("|")[0] for k in TR.files})
+
+
+@pytest.mark.parametrize("dname,ndt,tdt", DTYPES)
+@pytest.mark.parametrize("spec", GOLDEN_SPECS)
+def test_transforms_match_reference_golden(spec, dname, ndt, tdt):
+    """Inputs and outputs recorded from the unmodified reference (oracle/gen_golden.py)."""
+    c = make(us, spec)
+    p = f"{spec}|{dname}|"
+    keys = ["r"] + list(reversed(c.s_nodes))
+    got = c.from_cartesian(dev(TR[p + "x"]))
+    want = TR[p + "sph"]
+    assert np.array_equal(host(got["r"]), want[0])
+    for i, k in enumerate(keys[1:], start=1):
+        assert_angles_close(host(got[k]), want[i], f"{spec} {k}")
+    d = depth_of(c)
+    back = c.to_cartesian({k: dev(want[i]) for i, k in enumerate(keys)}, as_array=True)
+    assert_leaves_close(host(back), TR[p + "cart"], want[0], d, spec)
+    free = {k: dev(TR[p + "ang"][i]) for i, k in enumerate(c.s_nodes)}
+    assert_leaves_close(host(c.to_cartesian(free, as_array=True)), TR[p + "cart_free_no_r"], np.ones(1, ndt), d, spec)
+    free["r"] = dev(TR[p + "r"])
+    assert_leaves_close(host(c.to_cartesian(free, as_array=True)), TR[p + "cart_free"], TR[p + "r"], d, spec)
+
+
+@pytest.mark.parametrize("dname,ndt,tdt", DTYPES)
+@pytest.mark.parametrize("spec", GOLDEN_SPECS)
+def test_edge_vectors(spec, dname, ndt, tdt):
+    """zeros, signed zeros, axis points, 1e±30 (float32 overflows to inf exactly like NumPy)."""
+    c = make(us, spec)
+    p = f"{spec}|{dname}|"
+    keys = ["r"] + list(reversed(c.s_nodes))
+    got = c.from_cartesian(dev(TR[p + "edge_x"]))
+    want = TR[p + "edge_sph"]
+    assert np.array_equal(host(got["r"]), want[0], equal_nan=True)
+    for i, k in enumerate(keys[1:], start=1):
+        g, w = host(got[k]), want[i]
+        assert np.array_equal(np.isnan(g), np.isnan(w))
+        # atan2 conventions at ±0 / inf are IEEE in both; values within a few ulp, signs equal
+        ok = np.isnan(w) | (np.abs(g.astype(np.float64) - w.astype(np.float64)) <= 4 * np.spacing(np.abs(w)).astype(np.float64))
+        assert ok.all(), (spec, k)
+        assert np.array_equal(np.signbit(g[~np.isnan(w)]), np.signbit(w[~np.isnan(w)])), (spec, k)
+
+
+def test_known_answers_from_reference_doctests():
+    with open(os.path.join(GOLDEN, "kat.json")) as fh:
+        kat = json.load(fh)
+    c = us.create_spherical()
+    s = c.from_cartesian(torch.tensor([1.0, 2.0, 3.0], dtype=torch.float64, device=DEV))
+    assert list(s) == ["r", "phi", "theta"]
+    for key, val in kat["spherical_from_123_rounded"].items():
+        assert round(s[key].item(), 6) == val
+    assert s["r"].item().hex() == kat["spherical_from_123"]["r"]
+    back = c.to_cartesian(s)
+    assert {k: round(back[k].item(), 5) for k in c.c_nodes} == {0: 1.0, 1: 2.0, 2: 3.0}
+    for name, factory, x in (
+        ("hopf2", lambda: us.create_hopf(2), kat["hopf2_x"]),
+        ("standard3", lambda: us.create_standard(3), kat["hopf2_x"]),
+        ("standard_prime2", lambda: us.create_standard_prime(2), kat["standard_prime2_x"]),
+    ):
+        got = factory().from_cartesian(torch.tensor(x, dtype=torch.float64, device=DEV))
+        assert got["r"].item().hex() == kat[name]["r"]
+        for key, hexval in kat[name].items():
+            want = float.fromhex(hexval)
+            assert abs(got[key].item() - want) <= 4 * np.spacing(abs(want)), (name, key)
+
+
+# ---- the reference's own transform tests, on the CUDA path (tests/test_coordinates_transform.py) ----
+@pytest.mark.parametrize("shape", [(1,), (2, 3), (4, 5, 6)])
+def test_spherical_to_3d(shape):
+    r = torch.rand(shape, device=DEV)
+    theta = torch.rand(shape, device=DEV) * torch.pi
+    phi = torch.rand(shape, device=DEV) * 2 * torch.pi
+    actual = us.create_spherical().to_cartesian({"r": r, "theta": theta, "phi": phi})
+    rsin = r * torch.sin(theta)
+    for i, value in enumerate((rsin * torch.cos(phi), rsin * torch.sin(phi), r * torch.cos(theta))):
+        assert torch.allclose(value, actual[i], rtol=1e-3, atol=1e-3)
+    assert set(actual.keys()) == {0, 1, 2}
+
+
+@pytest.mark.parametrize("shape", [(1,), (2, 3), (4, 5, 6)])
+def test_cartesian_to_spherical_3d(shape):
+    x, y, z = (torch.rand(shape, device=DEV) * 2 - 1 for _ in range(3))
+    actual = us.create_spherical().from_cartesian({0: x, 1: y, 2: z})
+    r = torch.sqrt(x * x + y * y + z * z)
+    expected = {"r": r, "theta": torch.acos(z / r), "phi": torch.atan2(y, x)}
+    for key, value in expected.items():
+        assert torch.allclose(value, actual[key], rtol=1e-3, atol=1e-3)
+    assert set(actual.keys()) == {"r", "theta", "phi"}
+
+
+@pytest.mark.parametrize("shape", [(1,), (2, 3), (2, 4, 6)])
+@pytest.mark.parametrize("factory", [us.create_spherical, lambda: us.create_hopf(3), lambda: us.create_random(1), lambda: us.create_random(5)])
+def test_cartesian_to_spherical_round_trip(factory, shape):
+    c = factory()
+    x = torch.rand((c.c_ndim, *shape), device=DEV) * 2 - 1
+    back = c.to_cartesian(c.from_cartesian(x))
+    back = torch.stack([back[key] for key in range(c.c_ndim)])
+    assert torch.allclose(x, back, rtol=1e-6, atol=1e-6)
+
+
+# ---- input generality -------------------------------------------------------------------------
+@pytest.mark.parametrize("dname,ndt,tdt", DTYPES)
+def test_broadcast_inputs_keep_reference_shapes(dname, ndt, tdt):
+    """Inputs of different shapes: every output keeps the broadcast shape of what feeds it."""
+    c, t = us.create_from_branching_types("cbaa"), vo.tree_from_branching("cbaa")
+    rng = np.random.default_rng(3)
+    n = 7
+    ang = {}
+    for i, node in enumerate(c.s_nodes):
+        shp = [1] * c.s_ndim
+        shp[i] = n + i
+        ang[node] = rng.uniform(-3, 3, shp).astype(ndt)
+    want = vo.to_cartesian(t, dict(ang))
+    got = c.to_cartesian({k: dev(v) for k, v in ang.items()})
+    d = depth_of(c)
+    for i, leaf in enumerate(c.c_nodes):
+        assert tuple(got[leaf].shape) == want[leaf].shape, leaf
+        assert_leaves_close(host(got[leaf])[None], want[leaf][None], np.ones(1, ndt), d[i : i + 1], f"leaf {leaf}")
+    full = c.to_cartesian({k: dev(v) for k, v in ang.items()}, as_array=True)
+    wantf = vo.to_cartesian(t, dict(ang), as_array=True)
+    assert tuple(full.shape) == wantf.shape
+    assert_leaves_close(host(full), wantf, np.ones(1, ndt), d)
+    # r as python scalar, 0-d tensor and full tensor
+    for rv in (2.5, np.asarray(2.5, dtype=ndt), rng.uniform(0.5, 2, (n, 1, 1, 1)).astype(ndt)):
+        a = dict(ang)
+        a["r"] = rv
+        w = vo.to_cartesian(t, dict(a), as_array=True)
+        b = {k: dev(v) for k, v in ang.items()}
+        b["r"] = rv if isinstance(rv, float) else dev(rv)
+        g = c.to_cartesian(b, as_array=True)
+        assert tuple(g.shape) == w.shape
+        assert_leaves_close(host(g), w.astype(ndt), np.broadcast_to(np.asarray(rv, dtype=ndt), w.shape[1:]), d)
+    # from_cartesian with leaves of different shapes
+    xs = {leaf: rng.uniform(-1, 1, [n if j == i % 2 else 1 for j in range(2)]).astype(ndt) for i, leaf in enumerate(c.c_nodes)}
+    wants = vo.from_cartesian(t, xs)
+    gots = c.from_cartesian({k: dev(v) for k, v in xs.items()})
+    assert list(gots) == list(wants)
+    for k in wants:
+        assert tuple(gots[k].shape) == wants[k].shape, k
+        if k == "r":
+            assert np.array_equal(host(gots[k]), wants[k])
+        else:
+            assert_angles_close(host(gots[k]), wants[k], str(k))
+
+
+def test_strided_expanded_zero_dim_and_empty_inputs():
+    c, t = us.create_standard(3), vo.create_standard(3)
+    rng = np.random.default_rng(9)
+    big = rng.uniform(-1, 1, (4, 6, 10))
+    xt = dev(big)
+    view = xt[:, ::2, 1::3]  # non-contiguous rows
+    got = c.from_cartesian(view)
+    want = vo.from_cartesian(t, big[:, ::2, 1::3])
+    assert np.array_equal(host(got["r"]), want["r"])
+    for k in c.s_nodes:
+        assert_angles_close(host(got[k]), want[k])
+    # transposed leaves
+    tr = {i: xt[i].t() for i in range(4)}
+    got = c.from_cartesian(tr)
+    want = vo.from_cartesian(t, {i: big[i].T for i in range(4)})
+    assert np.array_equal(host(got["r"]), want["r"]) and got["r"].shape == (10, 6)
+    # expanded (stride 0) angle
+    th = {k: dev(rng.uniform(0, 3, (5,))) for k in c.s_nodes}
+    th["theta1"] = th["theta1"][:1].expand(5)
+    g = c.to_cartesian(th, as_array=True)
+    w = vo.to_cartesian(t, {k: host(v) for k, v in th.items()}, as_array=True)
+    assert_leaves_close(host(g), w, np.ones(1), depth_of(c))
+    # 0-d tensors
+    z = c.from_cartesian({i: dev(np.asarray(big[i, 0, 0])) for i in range(4)})
+    wz = vo.from_cartesian(t, {i: np.asarray(big[i, 0, 0]) for i in range(4)})
+    assert z["r"].shape == () and abs(z["r"].item() - float(wz["r"])) <= np.spacing(float(wz["r"]))
+    # empty batch
+    e = c.from_cartesian(torch.empty((4, 0), device=DEV))
+    assert all(v.shape == (0,) for v in e.values())
+    assert c.to_cartesian(e, as_array=True).shape == (4, 0)
+    # mixed dtypes promote like NumPy / torch
+    m = c.to_cartesian({"theta0": dev(np.float32([0.3])), "theta1": dev(np.float64([0.4])), "theta2": dev(np.float32([0.5]))})
+    assert m[0].dtype == torch.float64
+    # integer Cartesian input is promoted to the default float type
+    i32 = c.from_cartesian(torch.tensor([[1], [2], [3], [4]], device=DEV))
+    assert i32["r"].dtype == torch.get_default_dtype()
+    # outputs never alias inputs
+    x = dev(rng.uniform(-1, 1, (4, 16)))
+    s = c.from_cartesian(x)
+    assert all(v.data_ptr() < x.data_ptr() or v.data_ptr() >= x.data_ptr() + x.numel() * 8 for v in s.values())
+
+
+def test_odd_sizes_and_misaligned_rows():
+    """Row lengths that are not multiples of 16 bytes and batch sizes around the tile size."""
+    c, t = us.create_standard(9), vo.create_standard(9)
+    rng = np.random.default_rng(21)
+    for n in (1, 3, 31, 255, 1023, 1025, 4097, 65537, 300001):
+        for ndt in (np.float32, np.float64):
+            x = rng.uniform(-1, 1, (c.c_ndim, n)).astype(ndt)
+            want = vo.from_cartesian(t, x)
+            got = c.from_cartesian(dev(x))
+            if n >= 2:
+                assert np.array_equal(host(got["r"]), want["r"]), (n, ndt)
+            for k in c.s_nodes:
+                assert_angles_close(host(got[k]), want[k], f"n={n} {k}")
+            back = host(c.to_cartesian({k: dev(v) for k, v in want.items()}, as_array=True))
+            assert_leaves_close(back, vo.to_cartesian(t, want, as_array=True), want["r"], depth_of(c), f"n={n}")
+
+
+def test_stream_and_device_handling():
+    c = us.create_hopf(2)
+    x = torch.rand((4, 100000), device=DEV, dtype=torch.float64)
+    ref = c.from_cartesian(x)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        got = c.from_cartesian(x)
+        back = c.to_cartesian(got, as_array=True)
+    s.synchronize()
+    for k in ref:
+        assert torch.equal(ref[k], got[k])
+    assert torch.allclose(back, x, atol=1e-14)
+
+
+@pytest.mark.parametrize("spec,ndt,n", [("standard:9", np.float32, 1 << 22), ("hopf:3", np.float64, 1 << 21), ("random:32:0", np.float32, 1 << 20)])
+def test_million_point_parity(spec, ndt, n):
+    """The first 2^20+ points of the benchmark configs against the oracle."""
+    c, t = make(us, spec), vo.make(spec)
+    x = np.random.default_rng(0).uniform(-1, 1, (c.c_ndim, n)).astype(ndt)
+    want = vo.from_cartesian(t, x)
+    got = c.from_cartesian(dev(x))
+    assert np.array_equal(host(got["r"]), want["r"])
+    for k in c.s_nodes:
+        assert_angles_close(host(got[k]), want[k], f"{spec} {k}")
+    back = host(c.to_cartesian({k: dev(v) for k, v in want.items()}, as_array=True))
+    assert_leaves_close(back, vo.to_cartesian(t, want, as_array=True), want["r"], depth_of(c), spec)
+
+
+@pytest.mark.parametrize(
+    "spec,tdt,n",
+    [("standard:9", torch.float32, 256_000_000), ("hopf:3", torch.float64, 128_000_000),
+     ("standard_prime:8", torch.float64, 128_000_000), ("random:32:0", torch.float32, 64_000_000)],
+)
+def test_full_size_properties(spec, tdt, n):
+    """BASELINE.json sizes, checked through size-independent properties: r equals the norm that
+    torch computes in float64, the round trip returns the input, angles lie in their type's
+    range, and a re-run is bit-identical (deterministic kernels)."""
+    c = make(us, spec)
+    g = torch.Generator(device=DEV).manual_seed(1234)
+    x = torch.rand((c.c_ndim, n), device=DEV, dtype=tdt, generator=g).mul_(2).sub_(1)
+    sph = c.from_cartesian(x)
+    eps = torch.finfo(tdt).eps
+    chunk = 1 << 24
+    for lo in range(0, n, chunk):
+        sl = slice(lo, min(n, lo + chunk))
+        r64 = x[:, sl].double().square().sum(0).sqrt()
+        assert ((sph["r"][sl].double() - r64).abs() <= c.c_ndim * eps * r64).all()
+    pi = float(np.pi)
+    for node in c.s_nodes:
+        lo_, hi_ = {"a": (-pi, pi), "b": (0, pi), "b'": (-pi / 2, pi / 2), "c": (0, pi / 2)}[c.branching_types[node].value]
+        th = sph[node]
+        assert th.min().item() >= lo_ - 4 * eps and th.max().item() <= hi_ + 4 * eps, node
+    back = c.to_cartesian(sph, as_array=True)
+    for lo in range(0, n, chunk):
+        sl = slice(lo, min(n, lo + chunk))
+        err = (back[:, sl] - x[:, sl]).abs().amax(0) / sph["r"][sl]
+        assert err.max().item() <= 8 * eps
+    sph2 = c.from_cartesian(x)
+    assert all(torch.equal(sph[k], sph2[k]) for k in sph)
+    del back, sph2
+    torch.cuda.empty_cache()
