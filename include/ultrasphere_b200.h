@@ -164,6 +164,17 @@ US_API int us_separable_reduce(int dtype, int n_axes, const int64_t* len, const 
  */
 US_API int us_probe_fma_peak(int dtype, int iters, double* tflops);
 
+/*
+ * Test hook: evaluates the library's own float32 device math on n elements so that
+ * tests/test_gpu_math.py can bound its error against float64 and check the IEEE claims.
+ *   fn 0: out0 = sin(a), out1 = cos(a)          (the sincos used by us_to_cartesian)
+ *   fn 1: out0 = atan2(a, b)                    (the atan2 used by us_from_cartesian)
+ *   fn 2: out0 = library sqrt(a), out1 = __fsqrt_rn(a)   (must be bit-identical)
+ * All pointers are device pointers to n floats; out1 may be NULL for fn 1.
+ */
+US_API int us_math_probe_f32(int fn, int64_t n, const float* a_dev, const float* b_dev, float* out0_dev,
+                             float* out1_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,93 @@
+"""Accuracy of the library's own float32 device math (us_common.cuh) against float64, and the
+bit-exactness of its IEEE square root.  These bounds are what the parity tolerances rest on."""
+import numpy as np
+import pytest
+import torch
+
+from ultrasphere_b200 import _native
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def probe(fn, a, b=None):
+    at = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(DEV)
+    bt = None if b is None else torch.from_numpy(np.ascontiguousarray(b, dtype=np.float32)).to(DEV)
+    o0 = torch.empty_like(at)
+    o1 = torch.empty_like(at)
+    st = torch.cuda.current_stream().cuda_stream
+    _native.check(
+        _native.lib().us_math_probe_f32(fn, at.numel(), at.data_ptr(), None if bt is None else bt.data_ptr(), o0.data_ptr(), o1.data_ptr(), st),
+        "us_math_probe_f32",
+    )
+    return o0.cpu().numpy(), o1.cpu().numpy()
+
+
+def ulp_err(got, exact):
+    exact32 = exact.astype(np.float32)
+    return np.abs(got.astype(np.float64) - exact) / np.spacing(np.abs(exact32)).astype(np.float64)
+
+
+def test_sincos_accuracy():
+    rng = np.random.default_rng(0)
+    parts = [rng.uniform(-np.pi, np.pi, 2_000_000), rng.uniform(-100, 100, 2_000_000), rng.uniform(-32768, 32768, 2_000_000),
+             rng.uniform(-1e-3, 1e-3, 500_000)]
+    k = np.arange(-20000, 20001)
+    for d in (0, 1, -1, 3):  # floats next to multiples of pi/2: exact zeros of sin / cos
+        x = (k * (np.pi / 2)).astype(np.float32)
+        for _ in range(abs(d)):
+            x = np.nextafter(x, np.float32(np.inf if d > 0 else -np.inf))
+        parts.append(x.astype(np.float64))
+    x = np.concatenate(parts).astype(np.float32)
+    s, c = probe(0, x)
+    xd = x.astype(np.float64)
+    assert ulp_err(s, np.sin(xd)).max() <= 2.0
+    assert ulp_err(c, np.cos(xd)).max() <= 2.0
+    # relative accuracy is kept at the zeros (Cody–Waite with an exact first step)
+    assert (np.abs(s - np.sin(xd)) <= 2.5e-7 * np.abs(np.sin(xd))).all()
+    assert (np.abs(c - np.cos(xd)) <= 2.5e-7 * np.abs(np.cos(xd))).all()
+
+
+def test_sincos_slow_path_and_specials():
+    x = np.float32([32768.0, -32768.0, 1e6, -3.5e7, 1e20, 3.0e38, np.inf, -np.inf, np.nan, 0.0, -0.0])
+    s, c = probe(0, x)
+    xd = x.astype(np.float64)
+    with np.errstate(invalid="ignore"):
+        ws, wc = np.sin(xd), np.cos(xd)
+    fin = np.isfinite(xd)
+    assert ulp_err(s[fin], ws[fin]).max() <= 2.0 and ulp_err(c[fin], wc[fin]).max() <= 2.0
+    assert np.isnan(s[~fin]).all() and np.isnan(c[~fin]).all()
+
+
+def test_atan2_accuracy_and_conventions():
+    rng = np.random.default_rng(1)
+    y = np.concatenate([rng.uniform(-1, 1, 3_000_000), rng.uniform(-1, 1, 500_000) * 1e-6, rng.uniform(-1e20, 1e20, 500_000)])
+    x = np.concatenate([rng.uniform(-1, 1, 3_000_000), rng.uniform(-1, 1, 500_000), rng.uniform(-1e20, 1e20, 500_000)])
+    y, x = y.astype(np.float32), x.astype(np.float32)
+    a, _ = probe(1, y, x)
+    exact = np.arctan2(y.astype(np.float64), x.astype(np.float64))
+    assert ulp_err(a, exact).max() <= 4.5
+    assert (np.abs(a - exact) <= 3.5e-7 * np.abs(exact)).all()
+    # IEEE conventions (signed zeros, infinities, NaN, denormals, huge) via the libdevice path
+    sp = np.float32([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, np.nan, 1e-40, -1e-40, 3e38, -3e38, 1e-35])
+    yy, xx = [g.ravel() for g in np.meshgrid(sp, sp)]
+    a, _ = probe(1, yy, xx)
+    want = np.arctan2(yy, xx)
+    assert np.array_equal(np.isnan(a), np.isnan(want))
+    ok = ~np.isnan(want)
+    assert np.array_equal(np.signbit(a[ok]), np.signbit(want[ok]))
+    assert (np.abs(a[ok].astype(np.float64) - want[ok]) <= 4 * np.spacing(np.abs(want[ok])).astype(np.float64)).all()
+
+
+def test_sqrt_is_bit_identical_to_ieee():
+    rng = np.random.default_rng(2)
+    x = np.concatenate([
+        rng.uniform(0, 4, 4_000_000), 10.0 ** rng.uniform(-44, 38, 2_000_000), (rng.uniform(0, 1, 1_000_000) ** 2),
+        np.float64([0.0, -0.0, np.inf, np.nan, -1.0, 1e-45, 1.1754944e-38, 3.4028235e38, 1.0, 4.0, 2.0]),
+    ]).astype(np.float32)
+    mine, ieee = probe(2, x)
+    assert np.array_equal(mine.view(np.uint32)[~np.isnan(ieee)], ieee.view(np.uint32)[~np.isnan(ieee)])
+    assert np.array_equal(np.isnan(mine), np.isnan(ieee))
+    with np.errstate(invalid="ignore"):
+        want = np.sqrt(x)
+    assert np.array_equal(ieee[~np.isnan(want)], want[~np.isnan(want)])  # and both equal NumPy's sqrt

@@ -273,7 +273,7 @@ def test_strided_expanded_zero_dim_and_empty_inputs():
     w = vo.to_cartesian(t, {k: host(v) for k, v in th.items()}, as_array=True)
     assert_leaves_close(host(g), w, np.ones(1), depth_of(c))
     # 0-d tensors
-    z = c.from_cartesian({i: dev(np.asarray(big[i, 0, 0])) for i in range(4)})
+    z = c.from_cartesian({i: torch.tensor(float(big[i, 0, 0]), dtype=torch.float64, device=DEV) for i in range(4)})
     wz = vo.from_cartesian(t, {i: np.asarray(big[i, 0, 0]) for i in range(4)})
     assert z["r"].shape == () and abs(z["r"].item() - float(wz["r"])) <= np.spacing(float(wz["r"]))
     # empty batch

@@ -140,9 +140,8 @@ extern "C" int us_to_cartesian(const us_plan_t* plan, int dtype, int64_t n, int 
   p.r_mask = r_mask;
   if (n == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = try_launch_to_cartesian_tiled(p, dtype, st);
-  if (rc == 1) return 0;
-  if (rc != 0) return rc;
+  const int rc = try_launch_to_cartesian_tiled(p, dtype, st);
+  if (rc != kNotTaken) return rc;
   return launch_to_cartesian_strided(p, dtype, st);
 }
 
@@ -163,9 +162,8 @@ extern "C" int us_from_cartesian(const us_plan_t* plan, int dtype, int64_t n, in
   p.r_out = r_out_dev;
   if (n == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = try_launch_from_cartesian_tiled(p, dtype, st);
-  if (rc == 1) return 0;
-  if (rc != 0) return rc;
+  const int rc = try_launch_from_cartesian_tiled(p, dtype, st);
+  if (rc != kNotTaken) return rc;
   return launch_from_cartesian_strided(p, dtype, st);
 }
 
@@ -214,5 +212,52 @@ extern "C" int us_probe_fma_peak(int dtype, int iters, double* tflops) {
   US_CUDA_TRY(cudaGetLastError(), "fma_probe");
   const double flops = 2.0 * 8.0 * (double)iters * (double)blocks * threads;
   *tflops = flops / ((double)best * 1e-3) / 1e12;
+  return 0;
+}
+
+// ---- math test hook ------------------------------------------------------------------------
+namespace us {
+__global__ void __launch_bounds__(256) math_probe_f32(int fn, int64_t n, const float* a, const float* b, float* o0, float* o1) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  float x[4], y[4], r0[4], r1[4];
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    const int64_t j = (i + v < n) ? i + v : n - 1;
+    x[v] = a[j];
+    y[v] = b ? b[j] : 0.0f;
+  }
+  if (fn == 0) {
+    sincos_vec<4>(x, r0, r1);
+  } else if (fn == 1) {
+    atan2_vec<4>(x, y, r0);
+#pragma unroll
+    for (int v = 0; v < 4; ++v) r1[v] = 0.0f;
+  } else {
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      r0[v] = x[v];
+      r1[v] = __fsqrt_rn(x[v]);
+    }
+    sqrt_vec<4>(r0);
+  }
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    if (i + v < n) {
+      o0[i + v] = r0[v];
+      if (o1) o1[i + v] = r1[v];
+    }
+  }
+}
+}  // namespace us
+
+extern "C" int us_math_probe_f32(int fn, int64_t n, const float* a_dev, const float* b_dev, float* out0_dev,
+                                 float* out1_dev, void* stream) {
+  if (fn < 0 || fn > 2 || n < 0 || !a_dev || !out0_dev || (fn == 1 && !b_dev))
+    return fail(US_EINVAL, "us_math_probe_f32: bad arguments");
+  if (n == 0) return 0;
+  const int64_t blocks = (n + 1023) / 1024;
+  math_probe_f32<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(fn, n, a_dev, b_dev, out0_dev, out1_dev);
+  US_CUDA_TRY(cudaGetLastError(), "math_probe_f32 launch");
   return 0;
 }

@@ -24,8 +24,9 @@ static_assert(sizeof(XformParams) < 32000, "kernel parameter block must fit the 
 int launch_to_cartesian_strided(const XformParams& p, int dtype, cudaStream_t st);
 int launch_from_cartesian_strided(const XformParams& p, int dtype, cudaStream_t st);
 
-// contiguous fast path (us_transform_tma.cu); returns 1 if it took the launch, 0 if the caller
-// should use the strided kernels, <0 / >0 on error
+// contiguous fast path (us_transform_tiled.cu); returns 0 if it took the launch, kNotTaken if the
+// caller should use the strided kernels, any other value is an error status
+constexpr int kNotTaken = -1000;
 int try_launch_to_cartesian_tiled(const XformParams& p, int dtype, cudaStream_t st);
 int try_launch_from_cartesian_tiled(const XformParams& p, int dtype, cudaStream_t st);
 

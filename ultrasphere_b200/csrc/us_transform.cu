@@ -60,10 +60,11 @@ __global__ void __launch_bounds__(256) to_cartesian_strided(const __grid_constan
     const uint64_t w = p.plan.node[k];
     const int slot = node_slot(w);
     const T th = ld_stream((const T*)p.in[slot] + ix.off(p.in_mask[slot]));
-    T s, c;
-    sincos_t(th, &s, &c);
-    const T pc = mul_rn(cur, c);
-    const T ps = mul_rn(cur, s);
+    const T thv[1] = {th};
+    T sv[1], cv[1];
+    sincos_vec<1>(thv, sv, cv);
+    const T pc = mul_rn(cur, cv[0]);
+    const T ps = mul_rn(cur, sv[0]);
     T* oc = nullptr;
     T* os = nullptr;
     switch (node_kind(w)) {
@@ -104,7 +105,9 @@ __global__ void __launch_bounds__(256) from_cartesian_strided(const __grid_const
       const T sq = mul_rn(x, x);
       acc = (l == 0) ? sq : add_rn(acc, sq);
     }
-    st_stream((T*)p.r_out + i, sqrt_rn(acc));
+    T rv[1] = {acc};
+    sqrt_vec<1>(rv);
+    st_stream((T*)p.r_out + i, rv[0]);
   }
   // children before parents = the pre-order program walked backwards
   T stack[US_MAX_STACK];
@@ -138,10 +141,14 @@ __global__ void __launch_bounds__(256) from_cartesian_strided(const __grid_const
         vs = stack[--sp];
         break;
     }
+    const T vsv[1] = {vs}, vcv[1] = {vc};
+    T av[1], nv[1];
+    atan2_vec<1>(vsv, vcv, av);
     T* o = (T*)p.out[node_slot(w)];
-    if (o) st_stream(o + i, atan2_t(vs, vc));
+    if (o) st_stream(o + i, av[0]);
     // numpy: vector_norm(stack((sin, cos))) = sqrt(sin*sin + cos*cos), squares rounded first
-    cur = sqrt_rn(add_rn(mul_rn(vs, vs), mul_rn(vc, vc)));
+    norm2_vec<T, 1>(vsv, vcv, nv);
+    cur = nv[0];
   }
 }
 

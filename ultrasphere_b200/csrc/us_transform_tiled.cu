@@ -1,8 +1,386 @@
-// Contiguous fast path — placeholder until the TMA-staged persistent kernels land.
+// Cartesian <-> polyspherical transforms: contiguous fast path.
+//
+// Persistent kernels, one CTA of 256 threads per tile of 256*V points, grid = #SMs x resident
+// CTAs.  Each input array contributes one row of the tile; rows are brought into shared memory
+// by TMA bulk copies (cp.async.bulk, one per row, issued by warp 0) that complete on an mbarrier,
+// two stages deep, so that a full tile (tens of KB) is always in flight per CTA while the
+// previous one is being computed — memory-level parallelism comes from the copy engine, not from
+// registers.  Every thread then owns V consecutive points: it reads its V-wide slice of each row
+// with one 128-bit LDS, runs the compiled pre-order program (kernel-parameter constant bank,
+// warp-uniform control flow), and writes each result row with one 128-bit streaming STG.
+//
+// HBM traffic = algorithmic traffic: every input element is read once, every output written once
+// (2 * c_ndim * sizeof(T) bytes per point and direction).
+//
+// Reference semantics: src/ultrasphere/_coordinates.py:555-579 (from) and :636-656 (to).
 #include "us_common.cuh"
 #include "us_params.cuh"
 
 namespace us {
-int try_launch_to_cartesian_tiled(const XformParams&, int, cudaStream_t) { return 0; }
-int try_launch_from_cartesian_tiled(const XformParams&, int, cudaStream_t) { return 0; }
+
+constexpr int kTileThreads = 256;
+constexpr int kStages = 2;
+// 228 KB of shared memory per SM, 1 KB reserved per CTA: two CTAs of two stages each
+constexpr int kMaxStageBytes = 55 * 1024;
+
+// ---- PTX wrappers: mbarrier + TMA bulk copy -----------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// global -> shared bulk copy through the TMA unit; bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void tma_load_row(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+
+// ---- V-wide register tiles ------------------------------------------------------------------
+template <typename T, int V>
+struct alignas(sizeof(T) * V) Vec {
+  T v[V];
+};
+
+template <typename T, int V>
+__device__ __forceinline__ Vec<T, V> lds_vec(const T* row, int tid) {
+  return *reinterpret_cast<const Vec<T, V>*>(row + tid * V);
+}
+
+template <typename T, int V>
+__device__ __forceinline__ void stg_vec(T* dst, const Vec<T, V>& x) {
+  if constexpr (sizeof(T) * V == 16) {
+    const float4 f = *reinterpret_cast<const float4*>(&x);
+    __stcs(reinterpret_cast<float4*>(dst), f);
+  } else if constexpr (sizeof(T) * V == 8) {
+    const float2 f = *reinterpret_cast<const float2*>(&x);
+    __stcs(reinterpret_cast<float2*>(dst), f);
+  } else {
+    __stcs(reinterpret_cast<float*>(dst), *reinterpret_cast<const float*>(&x));
+  }
+}
+
+struct TileShared {
+  uint64_t full[kStages];
+};
+
+// Issue the copies of one tile (one elected thread: UBLKCP takes uniform operands, so spreading
+// the rows over lanes would only serialise them again): post the expected byte count, then one
+// bulk copy per input row.
+template <typename T>
+__device__ __forceinline__ void issue_tile(const XformParams& p, int n_rows, bool r_row, T* stage, int P,
+                                           int64_t first_point, uint64_t* bar, uint64_t policy) {
+  const uint32_t row_bytes = (uint32_t)(P * sizeof(T));
+  mbar_arrive_expect_tx(bar, row_bytes * (uint32_t)n_rows);
+  const int n_plain = r_row ? n_rows - 1 : n_rows;
+#pragma unroll 1
+  for (int row = 0; row < n_plain; ++row)
+    tma_load_row(stage + (size_t)row * P, (const T*)p.in[row] + first_point, row_bytes, bar, policy);
+  if (r_row) tma_load_row(stage + (size_t)n_plain * P, (const T*)p.r_in + first_point, row_bytes, bar, policy);
+}
+
+// =================================================================================================
+// to_cartesian
+// =================================================================================================
+template <typename T, int V, bool STACK>
+__global__ void __launch_bounds__(kTileThreads, 2) to_cartesian_tiled(const __grid_constant__ XformParams p, int64_t n_tiles) {
+  constexpr int P = kTileThreads * V;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int nn = p.plan.n_nodes;
+  const bool has_r = p.r_in != nullptr;
+  const int n_rows = nn + (has_r ? 1 : 0);
+  T* stage0 = reinterpret_cast<T*>(smem_raw);
+  const size_t stage_elems = (size_t)n_rows * P;
+  TileShared* sh = reinterpret_cast<TileShared*>(smem_raw + kStages * stage_elems * sizeof(T));
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(&sh->full[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const uint64_t policy = policy_evict_first();
+  // prologue: fill every stage
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+      const int64_t tile = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
+      if (tile < n_tiles) issue_tile<T>(p, n_rows, has_r, stage0 + s * stage_elems, P, tile * P, &sh->full[s], policy);
+    }
+  }
+  int it = 0;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int s = it % kStages;
+    const T* stage = stage0 + s * stage_elems;
+    mbar_wait(&sh->full[s], (uint32_t)((it / kStages) & 1));
+    const int64_t g = tile * P + (int64_t)tid * V;
+    Vec<T, V> cur;
+    if (has_r) {
+      cur = lds_vec<T, V>(stage + (size_t)nn * P, tid);
+    } else {
+#pragma unroll
+      for (int v = 0; v < V; ++v) cur.v[v] = T(1);
+    }
+    Vec<T, V> stack[STACK ? US_MAX_STACK : 1];
+    int sp = 0;
+    uint64_t w = p.plan.node[0];
+    Vec<T, V> th = lds_vec<T, V>(stage + (size_t)node_slot(w) * P, tid);
+#pragma unroll 2
+    for (int k = 0; k < nn; ++k) {
+      // fetch the next node's word and angles before the long sincos chains of this one
+      const uint64_t w_next = p.plan.node[(k + 1 < nn) ? k + 1 : k];
+      const Vec<T, V> th_next = lds_vec<T, V>(stage + (size_t)node_slot(w_next) * P, tid);
+      Vec<T, V> pc, ps, sn, cs;
+      sincos_vec<V>(th.v, sn.v, cs.v);
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        pc.v[v] = mul_rn(cur.v[v], cs.v[v]);
+        ps.v[v] = mul_rn(cur.v[v], sn.v[v]);
+      }
+      // data-flow form of the four node kinds (all predicates are warp-uniform):
+      //   a : both products are leaves, resume the most recently deferred branch
+      //   b : cos product is a leaf, continue along sin      b': sin product is a leaf, continue along cos
+      //   c : defer the sin product, continue along cos
+      const int kind = node_kind(w);
+      T* const oc = (kind == US_NODE_A || kind == US_NODE_B) ? (T*)p.out[node_cos_leaf(w)] : nullptr;
+      T* const os = (kind == US_NODE_A || kind == US_NODE_BP) ? (T*)p.out[node_sin_leaf(w)] : nullptr;
+      if constexpr (STACK) {
+        if (kind == US_NODE_C) stack[sp++] = ps;
+      }
+#pragma unroll
+      for (int v = 0; v < V; ++v) cur.v[v] = (kind == US_NODE_B) ? ps.v[v] : pc.v[v];
+      if constexpr (STACK) {
+        if (kind == US_NODE_A && sp > 0) cur = stack[--sp];
+      }
+      if (oc) stg_vec<T, V>(oc + g, pc);
+      if (os) stg_vec<T, V>(os + g, ps);
+      w = w_next;
+      th = th_next;
+    }
+    // every thread has finished reading this stage: refill it with the tile kStages ahead
+    __syncthreads();
+    if (tid == 0) {
+      const int64_t next = tile + (int64_t)kStages * gridDim.x;
+      if (next < n_tiles) issue_tile<T>(p, n_rows, has_r, stage0 + s * stage_elems, P, next * P, &sh->full[s], policy);
+    }
+  }
+}
+
+// =================================================================================================
+// from_cartesian
+// =================================================================================================
+template <typename T, int V, bool STACK>
+__global__ void __launch_bounds__(kTileThreads, 2) from_cartesian_tiled(const __grid_constant__ XformParams p, int64_t n_tiles) {
+  constexpr int P = kTileThreads * V;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int nn = p.plan.n_nodes;
+  const int n_rows = p.plan.n_leaves;
+  T* stage0 = reinterpret_cast<T*>(smem_raw);
+  const size_t stage_elems = (size_t)n_rows * P;
+  TileShared* sh = reinterpret_cast<TileShared*>(smem_raw + kStages * stage_elems * sizeof(T));
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(&sh->full[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const uint64_t policy = policy_evict_first();
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+      const int64_t tile = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
+      if (tile < n_tiles) issue_tile<T>(p, n_rows, false, stage0 + s * stage_elems, P, tile * P, &sh->full[s], policy);
+    }
+  }
+  T* const r_out = (T*)p.r_out;
+  int it = 0;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int s = it % kStages;
+    const T* stage = stage0 + s * stage_elems;
+    mbar_wait(&sh->full[s], (uint32_t)((it / kStages) & 1));
+    const int64_t g = tile * P + (int64_t)tid * V;
+    if (r_out) {
+      // leaves in c_nodes order, sequential, each square and each add rounded once
+      Vec<T, V> acc;
+      for (int l = 0; l < n_rows; ++l) {
+        const Vec<T, V> x = lds_vec<T, V>(stage + (size_t)l * P, tid);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const T sq = mul_rn(x.v[v], x.v[v]);
+          acc.v[v] = (l == 0) ? sq : add_rn(acc.v[v], sq);
+        }
+      }
+      sqrt_vec<V>(acc.v);
+      stg_vec<T, V>(r_out + g, acc);
+    }
+    Vec<T, V> stack[STACK ? US_MAX_STACK : 1];
+    int sp = 0;
+    Vec<T, V> cur;
+#pragma unroll
+    for (int v = 0; v < V; ++v) cur.v[v] = T(0);
+    for (int k = nn - 1; k >= 0; --k) {
+      const uint64_t w = p.plan.node[k];
+      Vec<T, V> vc, vs;
+      switch (node_kind(w)) {
+        case US_NODE_A:
+          if constexpr (STACK) {
+            if (k != nn - 1) stack[sp++] = cur;
+          }
+          vc = lds_vec<T, V>(stage + (size_t)node_cos_leaf(w) * P, tid);
+          vs = lds_vec<T, V>(stage + (size_t)node_sin_leaf(w) * P, tid);
+          break;
+        case US_NODE_B:
+          vc = lds_vec<T, V>(stage + (size_t)node_cos_leaf(w) * P, tid);
+          vs = cur;
+          break;
+        case US_NODE_BP:
+          vs = lds_vec<T, V>(stage + (size_t)node_sin_leaf(w) * P, tid);
+          vc = cur;
+          break;
+        default:
+          vc = cur;
+          if constexpr (STACK) vs = stack[--sp];
+          else vs = cur;
+          break;
+      }
+      Vec<T, V> th;
+      atan2_vec<V>(vs.v, vc.v, th.v);
+      T* o = (T*)p.out[node_slot(w)];
+      if (o) stg_vec<T, V>(o + g, th);
+      norm2_vec<T, V>(vs.v, vc.v, cur.v);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const int64_t next = tile + (int64_t)kStages * gridDim.x;
+      if (next < n_tiles) issue_tile<T>(p, n_rows, false, stage0 + s * stage_elems, P, next * P, &sh->full[s], policy);
+    }
+  }
+}
+
+// =================================================================================================
+// host side: eligibility, variant selection, launch, ragged tail
+// =================================================================================================
+static bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
+
+struct Variant {
+  const void* fn;
+  int v;
+};
+
+template <typename T, int V, bool STACK>
+static const void* to_fn() {
+  return (const void*)&to_cartesian_tiled<T, V, STACK>;
+}
+template <typename T, int V, bool STACK>
+static const void* from_fn() {
+  return (const void*)&from_cartesian_tiled<T, V, STACK>;
+}
+
+template <bool TO>
+static const void* pick(int dtype, int v, bool stack) {
+#define US_PICK(T, V)                                                                      \
+  return stack ? (TO ? to_fn<T, V, true>() : from_fn<T, V, true>()) : (TO ? to_fn<T, V, false>() : from_fn<T, V, false>())
+  if (dtype == US_F32) {
+    if (v == 4) { US_PICK(float, 4); }
+    if (v == 2) { US_PICK(float, 2); }
+    US_PICK(float, 1);
+  }
+  if (v == 2) { US_PICK(double, 2); }
+  US_PICK(double, 1);
+#undef US_PICK
+}
+
+static int sm_count() {
+  static int cached = 0;
+  if (!cached) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) cached = 148;
+  }
+  return cached;
+}
+
+template <bool TO>
+static int try_tiled(const XformParams& p, int dtype, cudaStream_t st) {
+  if (p.ndim != 1) return kNotTaken;
+  const int esz = dtype == US_F32 ? 4 : 8;
+  const int n_in = TO ? p.plan.n_nodes : p.plan.n_leaves;
+  const int n_out = TO ? p.plan.n_leaves : p.plan.n_nodes;
+  const int n_rows = n_in + ((TO && p.r_in) ? 1 : 0);
+  for (int i = 0; i < n_in; ++i)
+    if (p.in_mask[i] != 1u || !aligned16(p.in[i])) return kNotTaken;
+  if (TO && p.r_in && (p.r_mask != 1u || !aligned16(p.r_in))) return kNotTaken;
+  for (int i = 0; i < n_out; ++i)
+    if (p.out[i] && !aligned16(p.out[i])) return kNotTaken;
+  if (!TO && p.r_out && !aligned16(p.r_out)) return kNotTaken;
+  // widest vector whose two-stage tile still lets two CTAs share an SM
+  int v = 16 / esz;
+  while (v >= 1 && (int64_t)n_rows * kTileThreads * v * esz > kMaxStageBytes) v >>= 1;
+  if (v < 1) return kNotTaken;
+  const int P = kTileThreads * v;
+  const int64_t n_tiles = p.n / P;
+  if (n_tiles < 2 * sm_count()) return kNotTaken;  // small batches: the strided kernel is launch-bound anyway
+  const void* fn = pick<TO>(dtype, v, p.plan.max_stack > 0);
+  const size_t smem = (size_t)kStages * n_rows * P * esz + sizeof(TileShared);
+  US_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(smem)");
+  int per_sm = 0;
+  US_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kTileThreads, smem), "occupancy query");
+  if (per_sm < 1) return kNotTaken;
+  int64_t grid = (int64_t)sm_count() * per_sm;
+  if (grid > n_tiles) grid = n_tiles;
+  XformParams body = p;
+  int64_t tiles = n_tiles;
+  void* args[] = {(void*)&body, (void*)&tiles};
+  US_CUDA_TRY(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(kTileThreads), args, smem, st), "tiled launch");
+  // ragged tail (< one tile): the strided kernel on the remaining points
+  const int64_t done = n_tiles * P;
+  const int64_t rest = p.n - done;
+  if (rest > 0) {
+    XformParams tail = p;
+    const int64_t off = done * esz;
+    for (int i = 0; i < n_in; ++i) tail.in[i] = (const char*)p.in[i] + off;
+    for (int i = 0; i < n_out; ++i)
+      if (p.out[i]) tail.out[i] = (char*)p.out[i] + off;
+    if (p.r_in) tail.r_in = (const char*)p.r_in + off;
+    if (p.r_out) tail.r_out = (char*)p.r_out + off;
+    tail.n = rest;
+    tail.shape[0] = rest;
+    const int rc = TO ? launch_to_cartesian_strided(tail, dtype, st) : launch_from_cartesian_strided(tail, dtype, st);
+    if (rc != 0) return rc;
+  }
+  return 0;
+}
+
+int try_launch_to_cartesian_tiled(const XformParams& p, int dtype, cudaStream_t st) { return try_tiled<true>(p, dtype, st); }
+int try_launch_from_cartesian_tiled(const XformParams& p, int dtype, cudaStream_t st) { return try_tiled<false>(p, dtype, st); }
+
 }  // namespace us
