@@ -143,11 +143,10 @@ __global__ void __launch_bounds__(256) from_cartesian_strided(const __grid_const
     }
     const T vsv[1] = {vs}, vcv[1] = {vc};
     T av[1], nv[1];
-    atan2_vec<1>(vsv, vcv, av);
+    // theta = atan2(sin, cos); numpy's vector_norm(stack((sin, cos))) = sqrt(sin*sin + cos*cos)
+    node_from_vec<1>(vsv, vcv, av, nv);
     T* o = (T*)p.out[node_slot(w)];
     if (o) st_stream(o + i, av[0]);
-    // numpy: vector_norm(stack((sin, cos))) = sqrt(sin*sin + cos*cos), squares rounded first
-    norm2_vec<T, 1>(vsv, vcv, nv);
     cur = nv[0];
   }
 }

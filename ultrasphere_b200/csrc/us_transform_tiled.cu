@@ -1,13 +1,15 @@
 // Cartesian <-> polyspherical transforms: contiguous fast path.
 //
-// Persistent kernels, one CTA of 256 threads per tile of 256*V points, grid = #SMs x resident
-// CTAs.  Each input array contributes one row of the tile; rows are brought into shared memory
-// by TMA bulk copies (cp.async.bulk, one per row, issued by warp 0) that complete on an mbarrier,
-// two stages deep, so that a full tile (tens of KB) is always in flight per CTA while the
-// previous one is being computed — memory-level parallelism comes from the copy engine, not from
-// registers.  Every thread then owns V consecutive points: it reads its V-wide slice of each row
-// with one 128-bit LDS, runs the compiled pre-order program (kernel-parameter constant bank,
-// warp-uniform control flow), and writes each result row with one 128-bit streaming STG.
+// Persistent, warp-specialised kernels: grid = #SMs x resident CTAs, each CTA = 8 consumer warps
+// + 1 producer warp, looping over tiles of 256*V points.  Each input array contributes one row of
+// a tile; the producer brings rows into shared memory with TMA bulk copies (cp.async.bulk, one
+// per row) that complete on a "full" mbarrier, two stages deep, so a whole tile (tens of KB) is in
+// flight per CTA while the previous one is computed — memory-level parallelism comes from the
+// copy engine, not from registers.  Consumer warps never wait for each other: a warp that has
+// finished reading a stage arrives on that stage's "empty" mbarrier, and only the producer waits
+// for all eight arrivals before refilling it.  Every consumer thread owns V consecutive points:
+// one 128-bit LDS per input row, the compiled pre-order program (kernel-parameter constant bank,
+// warp-uniform control flow), one 128-bit streaming STG per output row.
 //
 // HBM traffic = algorithmic traffic: every input element is read once, every output written once
 // (2 * c_ndim * sizeof(T) bytes per point and direction).
@@ -18,7 +20,8 @@
 
 namespace us {
 
-constexpr int kTileThreads = 256;
+constexpr int kTileThreads = 256;                // consumer threads = points per tile / V
+constexpr int kBlockThreads = kTileThreads + 32;  // + one producer warp
 constexpr int kStages = 2;
 // 228 KB of shared memory per SM, 1 KB reserved per CTA: two CTAs of two stages each
 constexpr int kMaxStageBytes = 55 * 1024;
@@ -34,6 +37,9 @@ __device__ __forceinline__ void fence_mbar_init() {
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -88,10 +94,6 @@ __device__ __forceinline__ void stg_vec(T* dst, const Vec<T, V>& x) {
   }
 }
 
-struct TileShared {
-  uint64_t full[kStages];
-};
-
 // Issue the copies of one tile (one elected thread: UBLKCP takes uniform operands, so spreading
 // the rows over lanes would only serialise them again): post the expected byte count, then one
 // bulk copy per input row.
@@ -107,11 +109,50 @@ __device__ __forceinline__ void issue_tile(const XformParams& p, int n_rows, boo
   if (r_row) tma_load_row(stage + (size_t)n_plain * P, (const T*)p.r_in + first_point, row_bytes, bar, policy);
 }
 
+struct TileShared {
+  uint64_t full[kStages];   // producer -> consumers: the stage's bytes have landed (tx count)
+  uint64_t empty[kStages];  // consumers -> producer: all 8 consumer warps are done with the stage
+};
+
+__device__ __forceinline__ void init_barriers(TileShared* sh) {
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&sh->full[s], 1);
+      mbar_init(&sh->empty[s], kTileThreads / 32);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+}
+
+// The producer warp: one elected lane walks this CTA's tiles, waits until the stage it is about to
+// overwrite has been released, and issues the tile's copies.
+template <typename T>
+__device__ __forceinline__ void producer_loop(const XformParams& p, int n_rows, bool r_row, T* stage0, size_t stage_elems,
+                                              int P, int64_t n_tiles, TileShared* sh) {
+  if ((threadIdx.x & 31) != 0) return;
+  const uint64_t policy = policy_evict_first();
+  int it = 0;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int s = it % kStages;
+    if (it >= kStages) mbar_wait(&sh->empty[s], (uint32_t)(((it / kStages) - 1) & 1));
+    issue_tile<T>(p, n_rows, r_row, stage0 + s * stage_elems, P, tile * P, &sh->full[s], policy);
+  }
+}
+
+// A consumer warp is done with a stage: order its shared-memory reads, then one arrival.
+__device__ __forceinline__ void release_stage(TileShared* sh, int s) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(&sh->empty[s]);
+}
+
+
 // =================================================================================================
 // to_cartesian
 // =================================================================================================
 template <typename T, int V, bool STACK>
-__global__ void __launch_bounds__(kTileThreads, 2) to_cartesian_tiled(const __grid_constant__ XformParams p, int64_t n_tiles) {
+__global__ void __launch_bounds__(kBlockThreads, 2) to_cartesian_tiled(const __grid_constant__ XformParams p, int64_t n_tiles) {
   constexpr int P = kTileThreads * V;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int nn = p.plan.n_nodes;
@@ -120,21 +161,11 @@ __global__ void __launch_bounds__(kTileThreads, 2) to_cartesian_tiled(const __gr
   T* stage0 = reinterpret_cast<T*>(smem_raw);
   const size_t stage_elems = (size_t)n_rows * P;
   TileShared* sh = reinterpret_cast<TileShared*>(smem_raw + kStages * stage_elems * sizeof(T));
+  init_barriers(sh);
   const int tid = threadIdx.x;
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < kStages; ++s) mbar_init(&sh->full[s], 1);
-    fence_mbar_init();
-  }
-  __syncthreads();
-  const uint64_t policy = policy_evict_first();
-  // prologue: fill every stage
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < kStages; ++s) {
-      const int64_t tile = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
-      if (tile < n_tiles) issue_tile<T>(p, n_rows, has_r, stage0 + s * stage_elems, P, tile * P, &sh->full[s], policy);
-    }
+  if (tid >= kTileThreads) {
+    producer_loop<T>(p, n_rows, has_r, stage0, stage_elems, P, n_tiles, sh);
+    return;
   }
   int it = 0;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -185,12 +216,7 @@ __global__ void __launch_bounds__(kTileThreads, 2) to_cartesian_tiled(const __gr
       w = w_next;
       th = th_next;
     }
-    // every thread has finished reading this stage: refill it with the tile kStages ahead
-    __syncthreads();
-    if (tid == 0) {
-      const int64_t next = tile + (int64_t)kStages * gridDim.x;
-      if (next < n_tiles) issue_tile<T>(p, n_rows, has_r, stage0 + s * stage_elems, P, next * P, &sh->full[s], policy);
-    }
+    release_stage(sh, s);
   }
 }
 
@@ -198,7 +224,7 @@ __global__ void __launch_bounds__(kTileThreads, 2) to_cartesian_tiled(const __gr
 // from_cartesian
 // =================================================================================================
 template <typename T, int V, bool STACK>
-__global__ void __launch_bounds__(kTileThreads, 2) from_cartesian_tiled(const __grid_constant__ XformParams p, int64_t n_tiles) {
+__global__ void __launch_bounds__(kBlockThreads, 2) from_cartesian_tiled(const __grid_constant__ XformParams p, int64_t n_tiles) {
   constexpr int P = kTileThreads * V;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int nn = p.plan.n_nodes;
@@ -206,20 +232,11 @@ __global__ void __launch_bounds__(kTileThreads, 2) from_cartesian_tiled(const __
   T* stage0 = reinterpret_cast<T*>(smem_raw);
   const size_t stage_elems = (size_t)n_rows * P;
   TileShared* sh = reinterpret_cast<TileShared*>(smem_raw + kStages * stage_elems * sizeof(T));
+  init_barriers(sh);
   const int tid = threadIdx.x;
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < kStages; ++s) mbar_init(&sh->full[s], 1);
-    fence_mbar_init();
-  }
-  __syncthreads();
-  const uint64_t policy = policy_evict_first();
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < kStages; ++s) {
-      const int64_t tile = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
-      if (tile < n_tiles) issue_tile<T>(p, n_rows, false, stage0 + s * stage_elems, P, tile * P, &sh->full[s], policy);
-    }
+  if (tid >= kTileThreads) {
+    producer_loop<T>(p, n_rows, false, stage0, stage_elems, P, n_tiles, sh);
+    return;
   }
   T* const r_out = (T*)p.r_out;
   int it = 0;
@@ -247,42 +264,27 @@ __global__ void __launch_bounds__(kTileThreads, 2) from_cartesian_tiled(const __
     Vec<T, V> cur;
 #pragma unroll
     for (int v = 0; v < V; ++v) cur.v[v] = T(0);
+#pragma unroll 2
     for (int k = nn - 1; k >= 0; --k) {
       const uint64_t w = p.plan.node[k];
-      Vec<T, V> vc, vs;
-      switch (node_kind(w)) {
-        case US_NODE_A:
-          if constexpr (STACK) {
-            if (k != nn - 1) stack[sp++] = cur;
-          }
-          vc = lds_vec<T, V>(stage + (size_t)node_cos_leaf(w) * P, tid);
-          vs = lds_vec<T, V>(stage + (size_t)node_sin_leaf(w) * P, tid);
-          break;
-        case US_NODE_B:
-          vc = lds_vec<T, V>(stage + (size_t)node_cos_leaf(w) * P, tid);
-          vs = cur;
-          break;
-        case US_NODE_BP:
-          vs = lds_vec<T, V>(stage + (size_t)node_sin_leaf(w) * P, tid);
-          vc = cur;
-          break;
-        default:
-          vc = cur;
-          if constexpr (STACK) vs = stack[--sp];
-          else vs = cur;
-          break;
+      const int kind = node_kind(w);
+      // operands: a leaf comes from the tile, an internal child is the running norm (`cur`) or,
+      // for the sin child of a `c` node, the norm deferred on the stack
+      if constexpr (STACK) {
+        if (kind == US_NODE_A && k != nn - 1) stack[sp++] = cur;  // finished sibling subtree waits for its `c` parent
+      }
+      Vec<T, V> vc = cur, vs = cur;
+      if (kind == US_NODE_A || kind == US_NODE_B) vc = lds_vec<T, V>(stage + (size_t)node_cos_leaf(w) * P, tid);
+      if (kind == US_NODE_A || kind == US_NODE_BP) vs = lds_vec<T, V>(stage + (size_t)node_sin_leaf(w) * P, tid);
+      if constexpr (STACK) {
+        if (kind == US_NODE_C) vs = stack[--sp];
       }
       Vec<T, V> th;
-      atan2_vec<V>(vs.v, vc.v, th.v);
+      node_from_vec<V>(vs.v, vc.v, th.v, cur.v);
       T* o = (T*)p.out[node_slot(w)];
       if (o) stg_vec<T, V>(o + g, th);
-      norm2_vec<T, V>(vs.v, vc.v, cur.v);
     }
-    __syncthreads();
-    if (tid == 0) {
-      const int64_t next = tile + (int64_t)kStages * gridDim.x;
-      if (next < n_tiles) issue_tile<T>(p, n_rows, false, stage0 + s * stage_elems, P, next * P, &sh->full[s], policy);
-    }
+    release_stage(sh, s);
   }
 }
 
@@ -353,14 +355,14 @@ static int try_tiled(const XformParams& p, int dtype, cudaStream_t st) {
   const size_t smem = (size_t)kStages * n_rows * P * esz + sizeof(TileShared);
   US_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(smem)");
   int per_sm = 0;
-  US_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kTileThreads, smem), "occupancy query");
+  US_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kBlockThreads, smem), "occupancy query");
   if (per_sm < 1) return kNotTaken;
   int64_t grid = (int64_t)sm_count() * per_sm;
   if (grid > n_tiles) grid = n_tiles;
   XformParams body = p;
   int64_t tiles = n_tiles;
   void* args[] = {(void*)&body, (void*)&tiles};
-  US_CUDA_TRY(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(kTileThreads), args, smem, st), "tiled launch");
+  US_CUDA_TRY(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(kBlockThreads), args, smem, st), "tiled launch");
   // ragged tail (< one tile): the strided kernel on the remaining points
   const int64_t done = n_tiles * P;
   const int64_t rest = p.n - done;
