@@ -56,63 +56,96 @@ def parse() -> argparse.Namespace:
 # clocks
 # ----------------------------------------------------------------------------------------------
 class ClockSampler:
-    FIELDS = (
-        "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-        "clocks_event_reasons.sw_power_cap"
+    """SM clock, power and throttle reasons sampled DURING the timed region (NVML from a thread,
+    ~2 ms period; falls back to one nvidia-smi loop if NVML cannot be loaded)."""
+
+    REASONS = (
+        ("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4),
+        ("hw_power_brake_slowdown", 0x80),
     )
 
     def __init__(self, index: int) -> None:
-        self.rows: list[list[str]] = []
-        self.proc: subprocess.Popen | None = None
         self.index = index
+        self.samples: list[tuple[float, float, int]] = []
+        self.max_mhz: float | None = None
+        self._stop = threading.Event()
+        self._thread: threading.Thread | None = None
+        self._mode = "none"
+
+    def _physical_index(self) -> int:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.index])
+            except (ValueError, IndexError):
+                pass
+        return self.index
 
     def start(self) -> None:
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
-            )
-        except OSError:
-            self.proc = None
-            return
+            import pynvml
 
-        def pump() -> None:
-            assert self.proc is not None and self.proc.stdout is not None
-            for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
 
-        self.thread = threading.Thread(target=pump, daemon=True)
-        self.thread.start()
+            def pump() -> None:
+                while not self._stop.is_set():
+                    try:
+                        mhz = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        watts = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                        try:
+                            mask = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                        except Exception:
+                            mask = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                        self.samples.append((mhz, watts, mask))
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+
+            self._mode = "nvml"
+        except Exception:
+            fields = "clocks.sm,clocks.max.sm,power.draw"
+            try:
+                proc = subprocess.Popen(
+                    ["nvidia-smi", f"--id={self.index}", f"--query-gpu={fields}", "--format=csv,noheader,nounits", "-lms", "20"],
+                    stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+                )
+            except OSError:
+                return
+            self._proc = proc
+
+            def pump() -> None:
+                assert proc.stdout is not None
+                for line in proc.stdout:
+                    cells = [c.strip() for c in line.split(",")]
+                    try:
+                        self.samples.append((float(cells[0]), float(cells[2]), 0))
+                        self.max_mhz = float(cells[1])
+                    except (ValueError, IndexError):
+                        continue
+
+            self._mode = "nvidia-smi"
+        self._thread = threading.Thread(target=pump, daemon=True)
+        self._thread.start()
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, pw, reasons = [], [], [], set()
-        for row in self.rows:
-            if len(row) < 7:
-                continue
-            try:
-                sm.append(float(row[0]))
-                mx.append(float(row[1]))
-                pw.append(float(row[2]))
-            except ValueError:
-                continue
-            for name, cell in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), row[3:7]):
-                if cell.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        # "under load": samples drawing more than half of the peak power seen
-        hot = [s for s, p in zip(sm, pw) if p >= 0.5 * max(pw)] or sm
-        hot.sort()
-        return {"sm_mhz": hot[len(hot) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm), "reasons": sorted(reasons)}
+        self._stop.set()
+        if self._mode == "nvidia-smi":
+            self._proc.terminate()
+        if self._thread is not None:
+            self._thread.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples"], "source": self._mode}
+        peak_w = max(w for _, w, _ in self.samples)
+        hot = sorted(m for m, w, _ in self.samples if w >= 0.5 * peak_w) or sorted(m for m, _, _ in self.samples)
+        mask = 0
+        for _, _, m in self.samples:
+            mask |= m
+        return {
+            "sm_mhz": hot[len(hot) // 2], "sm_max_mhz": self.max_mhz, "power_w_max": peak_w, "samples": len(self.samples),
+            "reasons": [name for name, bit in self.REASONS if mask & bit], "source": self._mode,
+        }
 
 
 # ----------------------------------------------------------------------------------------------
