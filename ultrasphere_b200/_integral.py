@@ -327,8 +327,7 @@ def integrate(
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         if world > 1:
             sharded = True
-            lo_rank = (n0 * rank) // world
-            hi_rank = (n0 * (rank + 1)) // world
+            lo_rank, hi_rank = shard_rows(n0, rank, world)
     rest = 1
     for w in w_list[1:]:
         rest *= w.numel()
@@ -374,6 +373,11 @@ def integrate(
         probe = f({k: (v[:2] if k == nodes[0] else v) for k, v in xs.items()})
         out = torch.zeros(probe.shape[c.s_ndim :], dtype=torch.promote_types(probe.dtype, w_list[0].dtype), device=device)
     return _finish(out, group, sharded=sharded)
+
+
+def shard_rows(n_rows: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous share ``[lo, hi)`` of the leading grid axis owned by ``rank`` (may be empty)."""
+    return (n_rows * rank) // world, (n_rows * (rank + 1)) // world
 
 
 def _finish(result: torch.Tensor, group: Any | None, *, sharded: bool) -> torch.Tensor:
