@@ -123,6 +123,22 @@ US_API int us_to_cartesian(const us_plan_t* plan, int dtype, int64_t n, int ndim
                     uint32_t r_mask, void* const* out_dev, void* stream);
 
 /*
+ * Same as us_to_cartesian, with scratch for the broadcast case (an integrand inside integrate()
+ * passes s_ndim one-dimensional axes and asks for the full tensor grid): every angle operand
+ * that is at least 4x smaller than the launch gets its sin/cos evaluated ONCE into
+ * workspace_dev by a pre-pass, and the grid kernel then only looks them up, multiplies and
+ * writes.  Values are identical to us_to_cartesian (same sincos on the same angle values).
+ * us_to_cartesian_workspace_bytes returns the scratch needed (0: nothing to tabulate);
+ * workspace_dev must be 16-byte aligned; NULL / too small falls back to us_to_cartesian.
+ */
+US_API int64_t us_to_cartesian_workspace_bytes(const us_plan_t* plan, int dtype, int64_t n, int ndim,
+                                               const int64_t* shape, const uint32_t* angle_mask);
+US_API int us_to_cartesian_ws(const us_plan_t* plan, int dtype, int64_t n, int ndim, const int64_t* shape,
+                              const void* const* angle_dev, const uint32_t* angle_mask, const void* r_dev,
+                              uint32_t r_mask, void* const* out_dev, void* workspace_dev,
+                              int64_t workspace_bytes, void* stream);
+
+/*
  * r = sqrt(sum over leaves in c_nodes order of x^2)  (sequential, each square and each add
  * rounded once — bit-identical to numpy.linalg.vector_norm(axis=0), _coordinates.py:556-563);
  * per internal node, children first: theta = atan2(v_sin, v_cos), v = sqrt(v_sin^2 + v_cos^2)

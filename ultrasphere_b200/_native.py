@@ -56,6 +56,11 @@ _SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
         C.c_int,
         [C.POINTER(UsPlan), C.c_int, C.c_int64, C.c_int, _PI64, _PP, _PU32, C.c_void_p, C.c_uint32, _PP, C.c_void_p],
     ),
+    "us_to_cartesian_workspace_bytes": (C.c_int64, [C.POINTER(UsPlan), C.c_int, C.c_int64, C.c_int, _PI64, _PU32]),
+    "us_to_cartesian_ws": (
+        C.c_int,
+        [C.POINTER(UsPlan), C.c_int, C.c_int64, C.c_int, _PI64, _PP, _PU32, C.c_void_p, C.c_uint32, _PP, C.c_void_p, C.c_int64, C.c_void_p],
+    ),
     "us_from_cartesian": (
         C.c_int,
         [C.POINTER(UsPlan), C.c_int, C.c_int64, C.c_int, _PI64, _PP, _PU32, C.c_void_p, _PP, C.c_void_p],

@@ -162,6 +162,20 @@ def device_guard(device: torch.device) -> Any:
     return torch.cuda.device(device)
 
 
+_workspaces: dict[tuple[int, int], torch.Tensor] = {}
+
+
+def _workspace_for(device: torch.device, nbytes: int) -> torch.Tensor:
+    """Per-(device, stream) scratch owned by the shim (the library never allocates); grown on
+    demand and reused, which is safe because every use is ordered on that one stream."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), _stream_ptr(device))
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
 def _ptr(t: torch.Tensor | None) -> int | None:
     return None if t is None else t.data_ptr()
 
@@ -243,18 +257,33 @@ def _launch_to(
     for j, l in enumerate(members):
         out_ptrs[l] = base + j * row_bytes
     rt = geo.tensors[-1]
+    lib = _native.lib()
+    shape_arr = _native.i64_array(geo.shape)
+    mask_arr = _native.u32_array(geo.masks[:-1])
+    # broadcast operands (e.g. the 1-D quadrature axes an integrand receives): scratch for their
+    # sin/cos tables, so the grid kernel only looks up, multiplies and stores
+    ws_ptr, ws_bytes = None, 0
+    if len(geo.shape) > 1 or any(m != 1 for m in geo.masks[:-1]):
+        ws_bytes = int(
+            lib.us_to_cartesian_workspace_bytes(C.byref(ct.plan), _DTYPE_CODE[dtype], geo.n, len(geo.shape), shape_arr, mask_arr)
+        )
+        if ws_bytes:
+            ws = _workspace_for(device, ws_bytes)
+            ws_ptr, ws_bytes = ws.data_ptr(), ws.numel()
     with device_guard(device):
-        status = _native.lib().us_to_cartesian(
+        status = lib.us_to_cartesian_ws(
             C.byref(ct.plan),
             _DTYPE_CODE[dtype],
             geo.n,
             len(geo.shape),
-            _native.i64_array(geo.shape),
+            shape_arr,
             _native.void_p_array(in_ptrs),
-            _native.u32_array(geo.masks[:-1]),
+            mask_arr,
             _ptr(rt),
             geo.masks[-1],
             _native.void_p_array(out_ptrs),
+            ws_ptr,
+            ws_bytes,
             _stream_ptr(device),
         )
     _native.check(status, "us_to_cartesian")

@@ -122,9 +122,10 @@ extern "C" int us_plan_compile(int32_t n_nodes, const uint8_t* kinds, const int3
   return 0;
 }
 
-extern "C" int us_to_cartesian(const us_plan_t* plan, int dtype, int64_t n, int ndim, const int64_t* shape,
-                               const void* const* angle_dev, const uint32_t* angle_mask, const void* r_dev,
-                               uint32_t r_mask, void* const* out_dev, void* stream) {
+extern "C" int us_to_cartesian_ws(const us_plan_t* plan, int dtype, int64_t n, int ndim, const int64_t* shape,
+                                  const void* const* angle_dev, const uint32_t* angle_mask, const void* r_dev,
+                                  uint32_t r_mask, void* const* out_dev, void* workspace_dev,
+                                  int64_t workspace_bytes, void* stream) {
   static const char* who = "us_to_cartesian";
   XformParams p;
   memset(&p, 0, sizeof p);
@@ -140,9 +141,23 @@ extern "C" int us_to_cartesian(const us_plan_t* plan, int dtype, int64_t n, int 
   p.r_mask = r_mask;
   if (n == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  const int rc = try_launch_to_cartesian_tiled(p, dtype, st);
+  int rc = try_launch_to_cartesian_tiled(p, dtype, st);
+  if (rc != kNotTaken) return rc;
+  rc = try_launch_to_cartesian_bcast(p, dtype, workspace_dev, workspace_bytes, st);
   if (rc != kNotTaken) return rc;
   return launch_to_cartesian_strided(p, dtype, st);
+}
+
+extern "C" int us_to_cartesian(const us_plan_t* plan, int dtype, int64_t n, int ndim, const int64_t* shape,
+                               const void* const* angle_dev, const uint32_t* angle_mask, const void* r_dev,
+                               uint32_t r_mask, void* const* out_dev, void* stream) {
+  return us_to_cartesian_ws(plan, dtype, n, ndim, shape, angle_dev, angle_mask, r_dev, r_mask, out_dev, nullptr, 0, stream);
+}
+
+extern "C" int64_t us_to_cartesian_workspace_bytes(const us_plan_t* plan, int dtype, int64_t n, int ndim,
+                                                   const int64_t* shape, const uint32_t* angle_mask) {
+  if (!plan || !shape || !angle_mask || ndim < 1 || ndim > US_MAX_DIMS || (dtype != US_F32 && dtype != US_F64)) return 0;
+  return bcast_workspace_bytes(plan, dtype, n, ndim, shape, angle_mask);
 }
 
 extern "C" int us_from_cartesian(const us_plan_t* plan, int dtype, int64_t n, int ndim, const int64_t* shape,

@@ -14,6 +14,7 @@ struct XformParams {
   const void* r_in;                 // to only; nullptr => r = 1
   void* r_out;                      // from only; nullptr => not wanted
   uint32_t in_mask[US_MAX_LEAVES];  // bit d set: input spans launch dim d
+  const void* tab[US_MAX_LEAVES];   // to, broadcast path: (sin, cos) table of a broadcast angle, or nullptr
   uint32_t r_mask;
   int32_t ndim;
   int64_t n;
@@ -23,6 +24,10 @@ static_assert(sizeof(XformParams) < 32000, "kernel parameter block must fit the 
 
 int launch_to_cartesian_strided(const XformParams& p, int dtype, cudaStream_t st);
 int launch_from_cartesian_strided(const XformParams& p, int dtype, cudaStream_t st);
+
+// broadcast path of to_cartesian (us_transform_bcast.cu): sincos tables for broadcast angles
+int64_t bcast_workspace_bytes(const us_plan_t* plan, int dtype, int64_t n, int ndim, const int64_t* shape, const uint32_t* angle_mask);
+int try_launch_to_cartesian_bcast(XformParams& p, int dtype, void* workspace, int64_t workspace_bytes, cudaStream_t st);
 
 // contiguous fast path (us_transform_tiled.cu); returns 0 if it took the launch, kNotTaken if the
 // caller should use the strided kernels, any other value is an error status

@@ -16,20 +16,19 @@ namespace us {
 constexpr int kRedThreads = 256;
 constexpr int kRedWarps = kRedThreads / 32;
 constexpr int kMaxRedBlocks = 148 * 4;  // one wave at 4 resident CTAs per SM
-constexpr int kSeg = 2048;              // elements of the innermost axis per work item
 
 struct ReduceParams {
   const void* val;
   const void* w[US_MAX_DIMS];
   int64_t extent[US_MAX_DIMS];
   int32_t ndim;
-  int32_t m;        // trailing elements per node (rows kernel: power of two <= 32)
-  int32_t log2m;
+  int32_t m;        // trailing elements per node
+  int32_t lanes;    // rows kernel: active lanes per warp = largest multiple of m that is <= 32
   int32_t nseg;     // segments per innermost-axis row
   int64_t rows;     // product of extent[0..ndim-1)
   int64_t inner;    // extent[ndim-1]
   int64_t items;    // rows * nseg
-  double* partial;  // [gridDim.x][m]
+  double* partial;  // [blocks][m]
 };
 
 template <typename T>
@@ -37,104 +36,154 @@ __device__ __forceinline__ double ldw(const void* w, int64_t i) {
   return (double)__ldg((const T*)w + i);
 }
 
-// A warp walks a contiguous range of (row, segment) work items.  The row's outer weight
-// prod_{i<ndim-1} w_i[idx_i] is warp-uniform; the odometer idx[] is advanced per row instead of
-// re-dividing.  Lanes stride the innermost run of inner*m contiguous values; with m | 32 a lane
-// always lands on the same trailing index, so one accumulator per lane suffices.
+// Odometer over the outer axes: the warp-uniform weight prod_{i<ndim-1} w_i[idx_i] of a grid row.
+template <typename T>
+struct RowWalker {
+  int64_t idx[US_MAX_DIMS];
+  const ReduceParams& p;
+  __device__ __forceinline__ RowWalker(const ReduceParams& pp, int64_t row) : p(pp) {
+    int64_t rem = row;
+    for (int d = p.ndim - 2; d >= 0; --d) {
+      const int64_t e = p.extent[d];
+      const int64_t q = rem / e;
+      idx[d] = rem - q * e;
+      rem = q;
+    }
+  }
+  __device__ __forceinline__ double weight() const {
+    double w = 1.0;
+    for (int d = 0; d < p.ndim - 1; ++d) w *= ldw<T>(p.w[d], idx[d]);
+    return w;
+  }
+  __device__ __forceinline__ void next() {
+    for (int d = p.ndim - 2; d >= 0; --d) {
+      if (++idx[d] < p.extent[d]) break;
+      idx[d] = 0;
+    }
+  }
+};
+
+constexpr int kRowGroup = 4;  // rows a warp keeps in flight
+constexpr int kChunk = 4;     // strided loads per lane and row in flight (kRowGroup*kChunk loads)
+
+// Rows kernel (m <= 32).  A warp owns a contiguous range of grid rows.  The innermost run of a
+// row (inner*m contiguous values) is read by `lanes` lanes with stride `lanes`; because `lanes` is
+// a multiple of m, a lane always sees the same trailing index and the inner index advances by
+// lanes/m per step: one accumulator per lane, no divisions.  Loads of kRowGroup rows x kChunk
+// strides are issued before any is consumed (memory-level parallelism: 16 x 256 B per warp), the
+// innermost weights are loaded once per stride and shared by the rows of the group.
 template <typename T>
 __global__ void __launch_bounds__(kRedThreads) wreduce_rows(const __grid_constant__ ReduceParams p) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int64_t nwarps = (int64_t)gridDim.x * kRedWarps;
   const int64_t gw = (int64_t)blockIdx.x * kRedWarps + warp;
-  const int64_t per = (p.items + nwarps - 1) / nwarps;
-  int64_t it = gw * per;
-  const int64_t it_end = min(p.items, it + per);
+  const int64_t per = (p.rows + nwarps - 1) / nwarps;
+  int64_t row = gw * per;
+  const int64_t row_end = min(p.rows, row + per);
+  const int m = p.m, W = p.lanes;
+  const int lw = W / m;             // inner-index advance per stride
+  const int l0 = lane / m;          // this lane's inner index in stride 0
+  const bool active = lane < W;
+  const int64_t run = p.inner * m;  // contiguous values per row
+  const T* val = (const T*)p.val;
+  const void* wl = p.w[p.ndim - 1];
   double acc = 0.0;
-  if (it < it_end) {
-    const int nd = p.ndim;
-    int64_t row = it / p.nseg;
-    int seg = (int)(it - row * p.nseg);
+  if (row < row_end) {
+    RowWalker<T> walk(p, row);
+    for (; row < row_end; row += kRowGroup) {
+      double wrow[kRowGroup];
+      const T* base[kRowGroup];
+#pragma unroll
+      for (int r = 0; r < kRowGroup; ++r) {
+        const bool live = row + r < row_end;
+        wrow[r] = live ? walk.weight() : 0.0;
+        base[r] = val + (live ? row + r : row) * run;
+        if (live) walk.next();
+      }
+      double a[kRowGroup];
+#pragma unroll
+      for (int r = 0; r < kRowGroup; ++r) a[r] = 0.0;
+      int64_t lb = l0;  // inner index of this lane's first element in the current chunk
+      for (int64_t e0 = 0; e0 < run; e0 += (int64_t)kChunk * W, lb += (int64_t)kChunk * lw) {
+        T v[kRowGroup][kChunk];
+        double wv[kChunk];
+#pragma unroll
+        for (int j = 0; j < kChunk; ++j) {
+          const int64_t e = e0 + (int64_t)j * W + lane;
+          const bool ok = active && e < run;
+#pragma unroll
+          for (int r = 0; r < kRowGroup; ++r) v[r][j] = ok ? ld_stream(base[r] + e) : T(0);
+          wv[j] = ok ? ldw<T>(wl, lb + (int64_t)j * lw) : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < kChunk; ++j)
+#pragma unroll
+          for (int r = 0; r < kRowGroup; ++r) a[r] = fma(wv[j], (double)v[r][j], a[r]);
+      }
+#pragma unroll
+      for (int r = 0; r < kRowGroup; ++r) acc = fma(wrow[r], a[r], acc);
+    }
+  }
+  // lanes congruent mod m hold the same trailing index: shared-memory tree over lanes and warps
+  __shared__ double sm[kRedWarps][32];
+  sm[warp][lane] = active ? acc : 0.0;
+  __syncthreads();
+  if (threadIdx.x < m) {
+    double t = 0.0;
+    for (int wv = 0; wv < kRedWarps; ++wv)
+      for (int l = threadIdx.x; l < W; l += m) t += sm[wv][l];
+    p.partial[(int64_t)blockIdx.x * m + threadIdx.x] = t;
+  }
+}
+
+// Column kernel (m > 32): threads across the trailing index (coalesced), grid.y splits the grid
+// nodes; the node weight prod_i w_i[idx_i] is warp-uniform and advanced with an odometer, four
+// nodes' loads are in flight per thread.
+template <typename T>
+__global__ void __launch_bounds__(kRedThreads) wreduce_cols(const __grid_constant__ ReduceParams p,
+                                                            int64_t total_nodes, int64_t m64) {
+  const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t per = (total_nodes + gridDim.y - 1) / gridDim.y;
+  int64_t g = (int64_t)blockIdx.y * per;
+  const int64_t g1 = min(total_nodes, g + per);
+  const bool live_col = col < m64;
+  const T* val = (const T*)p.val;
+  double acc = 0.0;
+  if (g < g1) {
+    // odometer over ALL axes (the trailing index is the fastest one in memory)
     int64_t idx[US_MAX_DIMS];
     {
-      int64_t rem = row;
-      for (int d = nd - 2; d >= 0; --d) {
+      int64_t rem = g;
+      for (int d = p.ndim - 1; d >= 0; --d) {
         const int64_t e = p.extent[d];
         const int64_t q = rem / e;
         idx[d] = rem - q * e;
         rem = q;
       }
     }
-    double wrow = 1.0;
-    for (int d = 0; d < nd - 1; ++d) wrow *= ldw<T>(p.w[d], idx[d]);
-    const T* val = (const T*)p.val;
-    const void* wl = p.w[nd - 1];
-    const int64_t run = p.inner << p.log2m;  // contiguous values per row
-    for (; it < it_end; ++it) {
-      const int64_t e0 = (int64_t)seg * kSeg << p.log2m;
-      const int64_t e1 = min(run, e0 + ((int64_t)kSeg << p.log2m));
-      const T* base = val + row * run;
-      double a0 = 0.0, a1 = 0.0;
-      int64_t e = e0 + lane;
-      for (; e + 32 < e1; e += 64) {  // two independent loads in flight per lane
-        const double v0 = (double)ld_stream(base + e);
-        const double v1 = (double)ld_stream(base + e + 32);
-        a0 = fma(ldw<T>(wl, e >> p.log2m), v0, a0);
-        a1 = fma(ldw<T>(wl, (e + 32) >> p.log2m), v1, a1);
-      }
-      if (e < e1) a0 = fma(ldw<T>(wl, e >> p.log2m), (double)ld_stream(base + e), a0);
-      acc = fma(wrow, a0 + a1, acc);
-      if (++seg == p.nseg) {
-        seg = 0;
-        ++row;
-        // odometer carry over the outer axes, then refresh the row weight
-        for (int d = nd - 2; d >= 0; --d) {
-          if (++idx[d] < p.extent[d]) break;
-          idx[d] = 0;
-        }
-        wrow = 1.0;
-        for (int d = 0; d < nd - 1; ++d) wrow *= ldw<T>(p.w[d], idx[d]);
-      }
-    }
-  }
-  // lanes with equal (lane mod m) hold the same trailing index
-  for (int o = 16; o >= p.m; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
-  __shared__ double sm[kRedWarps][32];
-  if (lane < p.m) sm[warp][lane] = acc;
-  __syncthreads();
-  if (warp == 0 && lane < p.m) {
-    double t = sm[0][lane];
+    for (; g < g1; g += 4) {
+      double wg[4];
+      T v[4];
 #pragma unroll
-    for (int wv = 1; wv < kRedWarps; ++wv) t += sm[wv][lane];
-    p.partial[(int64_t)blockIdx.x * p.m + lane] = t;
-  }
-}
-
-// General trailing size: threads across the trailing index (coalesced), grid.y splits the grid
-// nodes; every node's weight product is recomputed per thread.  Correct for any m; the rows
-// kernel above is the fast path for m in {1,2,4,8,16,32} (real / complex scalars, short vectors).
-template <typename T>
-__global__ void __launch_bounds__(kRedThreads) wreduce_cols(const __grid_constant__ ReduceParams p,
-                                                            int64_t total_nodes, int64_t m64) {
-  const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t per = (total_nodes + gridDim.y - 1) / gridDim.y;
-  const int64_t g0 = (int64_t)blockIdx.y * per;
-  const int64_t g1 = min(total_nodes, g0 + per);
-  if (col >= m64) return;
-  const T* val = (const T*)p.val;
-  double acc = 0.0;
-  for (int64_t g = g0; g < g1; ++g) {
-    int64_t rem = g;
-    double wg = 1.0;
-    for (int d = p.ndim - 1; d >= 0; --d) {
-      const int64_t e = p.extent[d];
-      const int64_t q = rem / e;
-      wg *= ldw<T>(p.w[d], rem - q * e);
-      rem = q;
+      for (int r = 0; r < 4; ++r) {
+        const bool live = g + r < g1;
+        double w = live ? 1.0 : 0.0;
+        if (live) {
+          for (int d = 0; d < p.ndim; ++d) w *= ldw<T>(p.w[d], idx[d]);
+          for (int d = p.ndim - 1; d >= 0; --d) {
+            if (++idx[d] < p.extent[d]) break;
+            idx[d] = 0;
+          }
+        }
+        wg[r] = w;
+        v[r] = (live && live_col) ? ld_stream(val + (g + r) * m64 + col) : T(0);
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc = fma(wg[r], (double)v[r], acc);
     }
-    acc = fma(wg, (double)ld_stream(val + g * m64 + col), acc);
   }
-  p.partial[(int64_t)blockIdx.y * m64 + col] = acc;
+  if (live_col) p.partial[(int64_t)blockIdx.y * m64 + col] = acc;
 }
 
 template <typename T>
@@ -187,11 +236,11 @@ __global__ void __launch_bounds__(256) separable_reduce(const __grid_constant__ 
   }
 }
 
-static inline bool rows_ok(int64_t m) { return m >= 1 && m <= 32 && (m & (m - 1)) == 0; }
+static inline bool rows_ok(int64_t m) { return m >= 1 && m <= 32; }
 
-static int reduce_blocks(int64_t m, int64_t total_nodes, int64_t items, int* gx, int* gy) {
+static int reduce_blocks(int64_t m, int64_t total_nodes, int64_t rows, int* gx, int* gy) {
   if (rows_ok(m)) {
-    int64_t b = (items + kRedWarps - 1) / kRedWarps;
+    int64_t b = (rows + (int64_t)kRedWarps * kRowGroup - 1) / ((int64_t)kRedWarps * kRowGroup);
     *gx = (int)(b < 1 ? 1 : (b > kMaxRedBlocks ? kMaxRedBlocks : b));
     *gy = 1;
     return *gx;
@@ -237,16 +286,15 @@ extern "C" int us_weighted_reduce(int dtype, int ndim, const int64_t* extent, co
   }
   p.inner = extent[ndim - 1];
   p.rows = total / p.inner;
-  p.nseg = (int32_t)((p.inner + kSeg - 1) / kSeg);
-  p.items = p.rows * p.nseg;
+  p.nseg = 1;
+  p.items = p.rows;
   p.partial = (double*)scratch_dev;
   cudaStream_t st = (cudaStream_t)stream;
   int gx, gy;
-  const int nparts = reduce_blocks(m, total, p.items, &gx, &gy);
+  const int nparts = reduce_blocks(m, total, p.rows, &gx, &gy);
   if (rows_ok(m)) {
     p.m = (int32_t)m;
-    p.log2m = 0;
-    while ((1 << p.log2m) < m) ++p.log2m;
+    p.lanes = (int32_t)((32 / m) * m);
     if (dtype == US_F32)
       wreduce_rows<float><<<gx, kRedThreads, 0, st>>>(p);
     else
