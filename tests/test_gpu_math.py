@@ -91,3 +91,64 @@ def test_sqrt_is_bit_identical_to_ieee():
     with np.errstate(invalid="ignore"):
         want = np.sqrt(x)
     assert np.array_equal(ieee[~np.isnan(want)], want[~np.isnan(want)])  # and both equal NumPy's sqrt
+
+
+# ---- float64 node math ---------------------------------------------------------------------------
+def probe64(fn, a, b=None):
+    at = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(DEV)
+    bt = None if b is None else torch.from_numpy(np.ascontiguousarray(b, dtype=np.float64)).to(DEV)
+    o0 = torch.empty_like(at)
+    o1 = torch.empty_like(at)
+    st = torch.cuda.current_stream().cuda_stream
+    _native.check(
+        _native.lib().us_math_probe_f64(fn, at.numel(), at.data_ptr(), None if bt is None else bt.data_ptr(), o0.data_ptr(), o1.data_ptr(), st),
+        "us_math_probe_f64",
+    )
+    return o0.cpu().numpy(), o1.cpu().numpy()
+
+
+def test_f64_atan2_and_norm_accuracy():
+    """The float64 node op against 50-digit mpmath on a sample, and against NumPy on millions."""
+    import mpmath as mp
+
+    rng = np.random.default_rng(3)
+    n = 4_000_000
+    y = np.concatenate([rng.uniform(-1, 1, n), rng.uniform(-1, 1, n // 4) * 1e-9, rng.uniform(-1e100, 1e100, n // 4), rng.uniform(0, 1, n // 4)])
+    x = np.concatenate([rng.uniform(-1, 1, n), rng.uniform(-1, 1, n // 4), rng.uniform(-1e100, 1e100, n // 4), rng.uniform(-1, 1, n // 4) * 1e-7])
+    a, nrm = probe64(1, y, x)
+    want = np.arctan2(y, x)
+    d = np.abs(a - want) / np.spacing(np.abs(want))
+    assert d.max() <= 2.0, d.max()  # NumPy's own atan2 is within 1 ulp of exact
+    assert np.array_equal(nrm, np.sqrt(y * y + x * x))  # IEEE: squares, add, sqrt each rounded once
+    mp.mp.dps = 50
+    idx = rng.choice(len(y), 3000, replace=False)
+    worst = 0.0
+    for i in idx:
+        exact = mp.atan2(mp.mpf(float(y[i])), mp.mpf(float(x[i])))
+        err = abs(mp.mpf(float(a[i])) - exact) / mp.mpf(float(np.spacing(abs(float(exact)))))
+        worst = max(worst, float(err))
+    assert worst <= 1.5, worst  # libdevice documents 2 ulp for atan2
+    # IEEE conventions through the libdevice path
+    sp = np.float64([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, np.nan, 1e-320, -1e-320, 1e308, -1e308, 1e-200, 1e200])
+    yy, xx = [g.ravel() for g in np.meshgrid(sp, sp)]
+    a, nrm = probe64(1, yy, xx)
+    want = np.arctan2(yy, xx)
+    assert np.array_equal(np.isnan(a), np.isnan(want))
+    ok = ~np.isnan(want)
+    assert np.array_equal(np.signbit(a[ok]), np.signbit(want[ok]))
+    assert (np.abs(a[ok] - want[ok]) <= 2 * np.spacing(np.abs(want[ok]))).all()
+    with np.errstate(all="ignore"):
+        wn = np.sqrt(yy * yy + xx * xx)
+    assert np.array_equal(nrm, wn, equal_nan=True)
+
+
+def test_f64_sqrt_is_bit_identical_to_ieee():
+    rng = np.random.default_rng(4)
+    x = np.concatenate([
+        rng.uniform(0, 4, 6_000_000), 10.0 ** rng.uniform(-299, 299, 3_000_000), rng.uniform(0, 1, 1_000_000) ** 2,
+        np.nextafter(np.arange(1, 200001, dtype=np.float64) ** 2, 0), np.nextafter(np.arange(1, 200001, dtype=np.float64) ** 2, np.inf),
+        np.float64([1.0, 2.0, 4.0, 0.25, 1e-300 * 1.0000001, 9.99e299]),
+    ])
+    mine, ieee = probe64(2, x)
+    assert np.array_equal(mine, ieee)
+    assert np.array_equal(ieee, np.sqrt(x))

@@ -1,0 +1,40 @@
+"""Throughput of the secondary BASELINE configs (C1, C3, C4) at their full sizes: per-kernel
+time, points/s and fraction of the HBM roofline.  Prints one JSON object."""
+import json, os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ultrasphere_b200 as us
+from tests.helpers import make
+
+dev = torch.device("cuda:0")
+CONFIGS = [("spherical", torch.float64, 1_000_000), ("spherical", torch.float64, 64_000_000), ("hopf:3", torch.float64, 128_000_000),
+           ("standard_prime:8", torch.float64, 128_000_000), ("random:32:0", torch.float32, 64_000_000), ("standard:9", torch.float64, 128_000_000)]
+only = os.environ.get("US_ONLY")
+peak = 6536.4
+if os.path.isfile("MEASURED_PEAKS.json"):
+    peak = json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"]
+
+def t(fn, reps=5):
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    best = 1e9
+    for _ in range(reps):
+        e0.record(); fn(); e1.record(); e1.synchronize(); best = min(best, e0.elapsed_time(e1))
+    return best
+
+out = {}
+for spec, dt, n in CONFIGS:
+    if only and only not in spec:
+        continue
+    c = make(us, spec)
+    x = torch.rand((c.c_ndim, n), device=dev, dtype=dt) * 2 - 1
+    s = c.from_cartesian(x)
+    bpp = 2 * c.c_ndim * x.element_size()
+    tf = t(lambda: c.from_cartesian(x)); tt = t(lambda: c.to_cartesian(s, as_array=True))
+    out[f"{spec}|{str(dt)[6:]}|{n}"] = {
+        "from_ms": tf, "to_ms": tt, "from_gpts": n / tf / 1e6, "to_gpts": n / tt / 1e6,
+        "from_frac_hbm": n * bpp / tf / 1e6 / peak, "to_frac_hbm": n * bpp / tt / 1e6 / peak, "bytes_per_point": bpp,
+    }
+    del x, s
+    torch.cuda.empty_cache()
+print(json.dumps(out, indent=1))

@@ -29,10 +29,11 @@ from . import _native
 from ._coordinates import BranchingType, SphericalCoordinates, get_child
 from ._transform import _DTYPE_CODE, _stream_ptr, device_guard
 
-# A slab of the integrand's values is kept below this size unless the caller says otherwise;
-# 48 MiB of values plus the c_ndim-times larger Cartesian grid most integrands build still fit
-# the 126 MB L2 of a B200 for the common low-dimensional trees.
-DEFAULT_SLAB_BYTES = 48 << 20
+# The integrand is evaluated in slabs of the leading grid axis only to bound memory: a slab of
+# values is kept below this size unless the caller says otherwise (the c_ndim-times larger Cartesian
+# grid most integrands build comes on top).  Measured on B200 (tools/c5_breakdown.py): smaller,
+# L2-sized slabs are slower than one pass because of the extra launches, so the default is large.
+DEFAULT_SLAB_BYTES = 2 << 30
 
 
 def _check_xp(xp: Any) -> None:
@@ -294,7 +295,7 @@ def integrate(
 
     Extensions (keyword-only, defaults keep the reference behaviour):
       ``slab_bytes``  evaluate ``f`` on slabs of the leading grid axis of about this many bytes
-                      (default 48 MiB; ``0`` = one call)
+                      (default 2 GiB; ``0`` = one call)
       ``group``       a ``torch.distributed`` process group: the leading axis is sharded over its
                       ranks and the partial integrals are summed with one all-reduce
     """

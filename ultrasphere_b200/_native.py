@@ -73,6 +73,7 @@ _SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     "us_separable_reduce": (C.c_int, [C.c_int, C.c_int, _PI64, _PI64, _PP, _PP, _PP, C.c_void_p]),
     "us_probe_fma_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "us_math_probe_f32": (C.c_int, [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "us_math_probe_f64": (C.c_int, [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 EXPORTED = tuple(_SIGNATURES)

@@ -276,3 +276,46 @@ extern "C" int us_math_probe_f32(int fn, int64_t n, const float* a_dev, const fl
   US_CUDA_TRY(cudaGetLastError(), "math_probe_f32 launch");
   return 0;
 }
+
+namespace us {
+__global__ void __launch_bounds__(256) math_probe_f64(int fn, int64_t n, const double* a, const double* b, double* o0, double* o1) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (i >= n) return;
+  double x[2], y[2], r0[2], r1[2];
+#pragma unroll
+  for (int v = 0; v < 2; ++v) {
+    const int64_t j = (i + v < n) ? i + v : n - 1;
+    x[v] = a[j];
+    y[v] = b ? b[j] : 0.0;
+  }
+  if (fn == 1) {
+    // the kernels' node op: atan2 of (sin operand, cos operand) and their norm
+    node_from_vec<2>(x, y, r0, r1);
+  } else {
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      const bool ok = x[v] > 1e-300 && x[v] < 1e300;
+      r0[v] = ok ? sqrt_fast(x[v]) : __dsqrt_rn(x[v]);
+      r1[v] = __dsqrt_rn(x[v]);
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < 2; ++v) {
+    if (i + v < n) {
+      o0[i + v] = r0[v];
+      if (o1) o1[i + v] = r1[v];
+    }
+  }
+}
+}  // namespace us
+
+extern "C" int us_math_probe_f64(int fn, int64_t n, const double* a_dev, const double* b_dev, double* out0_dev,
+                                 double* out1_dev, void* stream) {
+  if (fn < 1 || fn > 2 || n < 0 || !a_dev || !out0_dev || (fn == 1 && !b_dev))
+    return fail(US_EINVAL, "us_math_probe_f64: bad arguments");
+  if (n == 0) return 0;
+  const int64_t blocks = (n + 511) / 512;
+  math_probe_f64<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(fn, n, a_dev, b_dev, out0_dev, out1_dev);
+  US_CUDA_TRY(cudaGetLastError(), "math_probe_f64 launch");
+  return 0;
+}

@@ -15,6 +15,8 @@
 // (2 * c_ndim * sizeof(T) bytes per point and direction).
 //
 // Reference semantics: src/ultrasphere/_coordinates.py:555-579 (from) and :636-656 (to).
+#include <stdlib.h>
+
 #include "us_common.cuh"
 #include "us_params.cuh"
 
@@ -347,6 +349,14 @@ static int try_tiled(const XformParams& p, int dtype, cudaStream_t st) {
   // widest vector whose two-stage tile still lets two CTAs share an SM
   int v = 16 / esz;
   while (v >= 1 && (int64_t)n_rows * kTileThreads * v * esz > kMaxStageBytes) v >>= 1;
+  {
+    static int forced_v = -1;  // US_TILE_V=<1|2|4>: tuning override (may leave one CTA per SM)
+    if (forced_v < 0) {
+      const char* e = getenv("US_TILE_V");
+      forced_v = e ? atoi(e) : 0;
+    }
+    if (forced_v > 0 && forced_v <= 16 / esz) v = forced_v;
+  }
   if (v < 1) return kNotTaken;
   const int P = kTileThreads * v;
   const int64_t n_tiles = p.n / P;
