@@ -191,7 +191,8 @@ US_API int us_probe_fma_peak(int dtype, int iters, double* tflops);
 US_API int us_math_probe_f32(int fn, int64_t n, const float* a_dev, const float* b_dev, float* out0_dev,
                              float* out1_dev, void* stream);
 
-/* float64 twin: fn 1: out0 = atan2(a, b); fn 2: out0 = library sqrt(a), out1 = __dsqrt_rn(a). */
+/* float64 twin: fn 0: out0 = sin(a), out1 = cos(a); fn 1: out0 = atan2(a, b), out1 = sqrt(a*a + b*b);
+ * fn 2: out0 = library sqrt(a), out1 = __dsqrt_rn(a). */
 US_API int us_math_probe_f64(int fn, int64_t n, const double* a_dev, const double* b_dev, double* out0_dev,
                              double* out1_dev, void* stream);
 

@@ -152,3 +152,43 @@ def test_f64_sqrt_is_bit_identical_to_ieee():
     mine, ieee = probe64(2, x)
     assert np.array_equal(mine, ieee)
     assert np.array_equal(ieee, np.sqrt(x))
+
+
+def test_f64_sincos_accuracy():
+    """<= 0.75 ulp against 50-digit mpmath on a sample (libdevice documents 2, NumPy measures ~0.5),
+    <= 1 ulp away from NumPy on millions of arguments, relative accuracy kept at the zeros."""
+    import mpmath as mp
+
+    rng = np.random.default_rng(5)
+    k = np.arange(-10000, 10001, dtype=np.float64)
+    near = k * (np.pi / 2)
+    x = np.concatenate([
+        rng.uniform(-np.pi, np.pi, 3_000_000), rng.uniform(-100, 100, 1_000_000), rng.uniform(-16384, 16384, 1_000_000),
+        rng.uniform(-1e-4, 1e-4, 200_000), near, np.nextafter(near, np.inf), np.nextafter(near, -np.inf),
+    ])
+    s, c = probe64(0, x)
+    ws, wc = np.sin(x), np.cos(x)
+    assert (np.abs(s - ws) <= 1.0 * np.spacing(np.abs(ws))).all()
+    assert (np.abs(c - wc) <= 1.0 * np.spacing(np.abs(wc))).all()
+    same = np.mean(s == ws), np.mean(c == wc)
+    assert min(same) > 0.9, same  # most values are bit-identical to NumPy's
+    mp.mp.dps = 50
+    idx = np.concatenate([rng.choice(5_000_000, 2500, replace=False), 5_200_000 + rng.choice(60_000, 1500, replace=False)])
+    worst = 0.0
+    for i in idx:
+        xv = mp.mpf(float(x[i]))
+        for got, exact in ((s[i], mp.sin(xv)), (c[i], mp.cos(xv))):
+            if exact == 0:
+                continue
+            err = abs(mp.mpf(float(got)) - exact) / mp.mpf(float(np.spacing(abs(float(exact)))))
+            worst = max(worst, float(err))
+    assert worst <= 0.75, worst
+    # slow path and specials
+    xs = np.float64([16384.0, -16384.0, 1e6, 1e9, -3.5e12, 1e22, 1e300, np.inf, -np.inf, np.nan, 0.0, -0.0])
+    s, c = probe64(0, xs)
+    with np.errstate(invalid="ignore"):
+        ws, wc = np.sin(xs), np.cos(xs)
+    fin = np.isfinite(xs)
+    assert (np.abs(s[fin] - ws[fin]) <= 2 * np.spacing(np.abs(ws[fin]))).all()
+    assert (np.abs(c[fin] - wc[fin]) <= 2 * np.spacing(np.abs(wc[fin]))).all()
+    assert np.isnan(s[~fin]).all() and np.isnan(c[~fin]).all()

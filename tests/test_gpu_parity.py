@@ -64,7 +64,7 @@ def assert_leaves_close(got: np.ndarray, want: np.ndarray, r: np.ndarray, depth:
     if got.dtype == np.float64:
         assert (err <= F64_ULP * np.spacing(rr)).all(), f"{what}: {np.max(err / np.spacing(rr))} ulp(r)"
         d = vo.ulp_distance(got, want)
-        lim = (F64_ULP + 2 * depth).reshape((-1,) + (1,) * (got.ndim - 1))
+        lim = (F64_ULP + depth).reshape((-1,) + (1,) * (got.ndim - 1))
         assert (d <= lim).all(), f"{what}: {d.max()} ulp element-wise"
     else:
         ok = (err <= F32_REL * np.abs(w)) | (err <= F32_REL * np.finfo(np.float32).eps * rr)

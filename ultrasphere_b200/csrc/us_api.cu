@@ -288,7 +288,9 @@ __global__ void __launch_bounds__(256) math_probe_f64(int fn, int64_t n, const d
     x[v] = a[j];
     y[v] = b ? b[j] : 0.0;
   }
-  if (fn == 1) {
+  if (fn == 0) {
+    sincos_vec<2>(x, r0, r1);
+  } else if (fn == 1) {
     // the kernels' node op: atan2 of (sin operand, cos operand) and their norm
     node_from_vec<2>(x, y, r0, r1);
   } else {
@@ -311,7 +313,7 @@ __global__ void __launch_bounds__(256) math_probe_f64(int fn, int64_t n, const d
 
 extern "C" int us_math_probe_f64(int fn, int64_t n, const double* a_dev, const double* b_dev, double* out0_dev,
                                  double* out1_dev, void* stream) {
-  if (fn < 1 || fn > 2 || n < 0 || !a_dev || !out0_dev || (fn == 1 && !b_dev))
+  if (fn < 0 || fn > 2 || n < 0 || !a_dev || !out0_dev || (fn == 1 && !b_dev))
     return fail(US_EINVAL, "us_math_probe_f64: bad arguments");
   if (n == 0) return 0;
   const int64_t blocks = (n + 511) / 512;
