@@ -3,7 +3,7 @@ golden vectors of the unmodified reference.  Needs a B200: run with ``-m gpu``.
 
 Tolerances (see tests/helpers.py and DESIGN.md "Tolerances"):
   float64  r bit-identical; angles <= 4 ulp; leaves |dx| <= 4 ulp(r)  [r = norm of the point]
-           and element-wise <= 4 + 2*depth ulp (every ancestor contributes one sin/cos whose
+           and element-wise <= 4 + depth ulp (every ancestor contributes one sin/cos whose
            last-bit rounding differs between libdevice and NumPy's SIMD kernels)
   float32  r bit-identical; angles and leaves <= 2e-6 relative element-wise (floor: 2e-6 * r
            absolute for leaves that are exact zeros of sin/cos)

@@ -172,6 +172,8 @@ class SphericalCoordinates[TSpherical, TCartesian]:
         self.sin_edges = [e for e in tree.edges if tree.edges[e]["type"] == "sin"]
         self._root = order[0]
         self._plan: Any = None  # compiled lazily by _plan.plan_for(self)
+        # leaves are exactly 0..c_ndim-1 in order: a (c_ndim, N) tensor can be addressed row-wise
+        self.is_c_keys_sorted_range = list(self.c_nodes) == list(range(len(self.c_nodes)))
 
     # ---- identity ----------------------------------------------------------------------
     def __hash__(self) -> int:

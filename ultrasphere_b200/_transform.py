@@ -194,6 +194,9 @@ def to_cartesian(c: SphericalCoordinates[Any, Any], spherical: Mapping[Any, Any]
             return torch.stack([r_in], dim=0)
         return {c.c_nodes[0]: r_in}
     r_is_tensor = isinstance(r_in, torch.Tensor)
+    fast = _to_cartesian_dense(c, angles_in, r_in, r_is_tensor, as_array)
+    if fast is not None:
+        return fast
     device = _require_cuda_tensors(angles_in + ([r_in] if r_is_tensor else []), "to_cartesian")
     dtype = _compute_dtype(angles_in + ([r_in] if r_is_tensor else []))
     if not r_is_tensor:
@@ -227,6 +230,60 @@ def to_cartesian(c: SphericalCoordinates[Any, Any], spherical: Mapping[Any, Any]
         for j, l in enumerate(members):
             result[l] = out[j]
     return {leaf: result[i] for i, leaf in enumerate(c.c_nodes)}
+
+
+def _to_cartesian_dense(
+    c: SphericalCoordinates[Any, Any], angles: list[Any], r: Any, r_is_tensor: bool, as_array: bool
+) -> Any:
+    """The common case with the least host work: every operand a dense CUDA tensor of one shape
+    and one float dtype (r absent, 1, or such a tensor too).  Returns None if the case is not this
+    one; the general path then validates, promotes and broadcasts."""
+    first = angles[0]
+    if not isinstance(first, torch.Tensor) or not first.is_cuda:
+        return None
+    dtype, shape, device = first.dtype, first.shape, first.device
+    code = _DTYPE_CODE.get(dtype)
+    if code is None:
+        return None
+    if r_is_tensor:
+        ops = angles + [r]
+    elif r == 1:
+        ops = angles
+    else:
+        return None
+    for t in ops:
+        if (
+            not isinstance(t, torch.Tensor)
+            or t.dtype != dtype
+            or t.shape != shape
+            or t.device != device
+            or not t.is_contiguous()
+        ):
+            return None
+    ct = plan_for(c)
+    n = first.numel()
+    out = torch.empty((ct.n_leaves, *shape), dtype=dtype, device=device)
+    if n:
+        row_bytes = n * out.element_size()
+        base = out.data_ptr()
+        with device_guard(device):
+            status = _native.lib().us_to_cartesian(
+                C.byref(ct.plan),
+                code,
+                n,
+                1,
+                _native.i64_array([n]),
+                _native.void_p_array([a.data_ptr() for a in angles]),
+                _native.u32_array([1] * ct.n_nodes),
+                r.data_ptr() if r_is_tensor else None,
+                1,
+                _native.void_p_array([base + i * row_bytes for i in range(ct.n_leaves)]),
+                _stream_ptr(device),
+            )
+        _native.check(status, "us_to_cartesian")
+    if as_array:
+        return out
+    return dict(zip(c.c_nodes, out.unbind(0)))
 
 
 def _launch_to(
@@ -293,7 +350,79 @@ def _launch_to(
 # --------------------------------------------------------------------------------------
 # from_cartesian
 # --------------------------------------------------------------------------------------
+def _from_cartesian_dense(c: SphericalCoordinates[Any, Any], cartesian: Any) -> dict[Any, Any] | None:
+    """Least host work for the two common inputs: one dense ``(c_ndim, *shape)`` CUDA tensor, or a
+    mapping of dense equal-shape CUDA tensors.  None if the input is anything else."""
+    ct_nodes = c.c_nodes
+    if isinstance(cartesian, torch.Tensor):
+        x = cartesian
+        if (
+            not x.is_cuda
+            or x.dim() < 1
+            or x.shape[0] != len(ct_nodes)
+            or not x.is_contiguous()
+            or not c.is_c_keys_sorted_range
+        ):
+            return None
+        dtype, shape, device = x.dtype, x.shape[1:], x.device
+        n = x.numel() // len(ct_nodes)
+        row = n * x.element_size()
+        in_ptrs = [x.data_ptr() + i * row for i in range(len(ct_nodes))]
+    else:
+        try:
+            leaves = [cartesian[k] for k in ct_nodes]
+        except (KeyError, IndexError, TypeError):
+            return None
+        first = leaves[0]
+        if not isinstance(first, torch.Tensor) or not first.is_cuda:
+            return None
+        dtype, shape, device = first.dtype, first.shape, first.device
+        for t in leaves:
+            if (
+                not isinstance(t, torch.Tensor)
+                or t.dtype != dtype
+                or t.shape != shape
+                or t.device != device
+                or not t.is_contiguous()
+            ):
+                return None
+        n = first.numel()
+        in_ptrs = [t.data_ptr() for t in leaves]
+    code = _DTYPE_CODE.get(dtype)
+    if code is None:
+        return None
+    ct = plan_for(c)
+    out = torch.empty((ct.n_nodes + 1, *shape), dtype=dtype, device=device)
+    if n:
+        row_bytes = n * out.element_size()
+        base = out.data_ptr()
+        with device_guard(device):
+            status = _native.lib().us_from_cartesian(
+                C.byref(ct.plan),
+                code,
+                n,
+                1,
+                _native.i64_array([n]),
+                _native.void_p_array(in_ptrs),
+                _native.u32_array([1] * ct.n_leaves),
+                base,
+                _native.void_p_array([base + (1 + s) * row_bytes for s in range(ct.n_nodes)]),
+                _stream_ptr(device),
+            )
+        _native.check(status, "us_from_cartesian")
+    rows = out.unbind(0)
+    result: dict[Any, Any] = {"r": rows[0]}
+    s_nodes = c.s_nodes
+    for s in range(ct.n_nodes - 1, -1, -1):  # dict order: "r", then children before parents
+        result[s_nodes[s]] = rows[1 + s]
+    return result
+
+
 def from_cartesian(c: SphericalCoordinates[Any, Any], cartesian: Any) -> dict[Any, Any]:
+    if c.s_ndim > 0:
+        fast = _from_cartesian_dense(c, cartesian)
+        if fast is not None:
+            return fast
     leaves_in = [cartesian[k] for k in c.c_nodes]  # mapping, or a tensor indexed by leaf id
     if c.s_ndim == 0:
         return {"r": leaves_in[0]}

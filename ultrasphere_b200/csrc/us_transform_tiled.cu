@@ -17,6 +17,8 @@
 // Reference semantics: src/ultrasphere/_coordinates.py:555-579 (from) and :636-656 (to).
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "us_common.cuh"
 #include "us_params.cuh"
 
@@ -27,6 +29,7 @@ constexpr int kBlockThreads = kTileThreads + 32;  // + one producer warp
 constexpr int kStages = 2;
 // 228 KB of shared memory per SM, 1 KB reserved per CTA: two CTAs of two stages each
 constexpr int kMaxStageBytes = 55 * 1024;
+constexpr int kSmemCeiling = 2 * kMaxStageBytes + 1024;
 
 // ---- PTX wrappers: mbarrier + TMA bulk copy -----------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -333,6 +336,41 @@ static int sm_count() {
   return cached;
 }
 
+// cudaFuncSetAttribute + the occupancy query cost a few microseconds each; their result only
+// depends on (kernel, dynamic shared memory, device), so it is computed once and remembered.
+static int resident_ctas(const void* fn, size_t smem, int* per_sm) {
+  struct Entry {
+    const void* fn;
+    size_t smem;
+    int dev, per_sm;
+  };
+  static Entry cache[128];
+  static int used = 0;
+  static std::mutex lock;
+  int dev = 0;
+  US_CUDA_TRY(cudaGetDevice(&dev), "cudaGetDevice");
+  std::lock_guard<std::mutex> guard(lock);
+  for (int i = 0; i < used; ++i)
+    if (cache[i].fn == fn && cache[i].smem == smem && cache[i].dev == dev) {
+      *per_sm = cache[i].per_sm;
+      return 0;
+    }
+  // the attribute is a ceiling: only ever raise it, or a later, smaller tree would lock out a wider one
+  size_t ceiling = 0;
+  for (int i = 0; i < used; ++i)
+    if (cache[i].fn == fn && cache[i].dev == dev && cache[i].smem > ceiling) ceiling = cache[i].smem;
+  if (smem > ceiling)
+    US_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(smem)");
+  US_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, fn, kBlockThreads, smem), "occupancy query");
+  if (used < 128) {
+    cache[used++] = Entry{fn, smem, dev, *per_sm};
+  } else {
+    // table full (128 distinct kernel/tree-width pairs): keep working, just without the shortcut
+    US_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCeiling), "cudaFuncSetAttribute(smem)");
+  }
+  return 0;
+}
+
 template <bool TO>
 static int try_tiled(const XformParams& p, int dtype, cudaStream_t st) {
   if (p.ndim != 1) return kNotTaken;
@@ -363,9 +401,8 @@ static int try_tiled(const XformParams& p, int dtype, cudaStream_t st) {
   if (n_tiles < 2 * sm_count()) return kNotTaken;  // small batches: the strided kernel is launch-bound anyway
   const void* fn = pick<TO>(dtype, v, p.plan.max_stack > 0);
   const size_t smem = (size_t)kStages * n_rows * P * esz + sizeof(TileShared);
-  US_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(smem)");
   int per_sm = 0;
-  US_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kBlockThreads, smem), "occupancy query");
+  if (int rc = resident_ctas(fn, smem, &per_sm)) return rc;
   if (per_sm < 1) return kNotTaken;
   int64_t grid = (int64_t)sm_count() * per_sm;
   if (grid > n_tiles) grid = n_tiles;
