@@ -174,6 +174,23 @@ US_API int us_separable_reduce(int dtype, int n_axes, const int64_t* len, const 
                         void* const* out_dev, void* stream);
 
 /*
+ * ---- "next" row of the path: the producer of transform inputs ----
+ * Uniform points in the unit ball (surface = 0) or on the unit sphere (surface = 1) of dimension
+ * `dim`, written as `dim` arrays of n elements (reference: src/ultrasphere/_random.py:16-57, which
+ * samples with NumPy on the host and copies to the device).  Philox4x32-10 keyed by `seed`; the
+ * value of point i depends only on (seed, i).  Distribution parity, not bit parity: the reference's
+ * stream is NumPy's PCG64.
+ */
+US_API int us_random_ball(int dtype, int dim, int64_t n, uint64_t seed, int surface, void* const* out_dev,
+                          void* stream);
+
+/*
+ * out_k[i] ~ U[lo_k, hi_k) for k < count (per-angle uniform sampling, _random.py:170-189).
+ */
+US_API int us_random_uniform(int dtype, int count, int64_t n, uint64_t seed, const double* lo,
+                             const double* hi, void* const* out_dev, void* stream);
+
+/*
  * Measurement helper: runs a dependent-free DFMA (dtype=US_F64) or FFMA (US_F32) loop on every
  * SM and returns the achieved TFLOP/s in *tflops (this one call synchronises).  Used by bench.py
  * as the denominator for the FP64-pipe-bound kernels (MEASURED_PEAKS.json has no FP64 entry).

@@ -17,6 +17,7 @@ from ._creation import (
     create_standard_prime,
 )
 from ._integral import integrate, roots, separable_reduce, weighted_reduce
+from ._random import random_ball
 
 __version__ = "0.1.0"
 
@@ -33,6 +34,7 @@ __all__ = [
     "get_child",
     "get_parent",
     "integrate",
+    "random_ball",
     "roots",
     "separable_reduce",
     "weighted_reduce",

@@ -71,6 +71,11 @@ _SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
         [C.c_int, C.c_int, _PI64, _PP, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p],
     ),
     "us_separable_reduce": (C.c_int, [C.c_int, C.c_int, _PI64, _PI64, _PP, _PP, _PP, C.c_void_p]),
+    "us_random_ball": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_uint64, C.c_int, _PP, C.c_void_p]),
+    "us_random_uniform": (
+        C.c_int,
+        [C.c_int, C.c_int, C.c_int64, C.c_uint64, C.POINTER(C.c_double), C.POINTER(C.c_double), _PP, C.c_void_p],
+    ),
     "us_probe_fma_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "us_math_probe_f32": (C.c_int, [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "us_math_probe_f64": (C.c_int, [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
