@@ -371,3 +371,23 @@ def test_full_size_properties(spec, tdt, n):
     assert all(torch.equal(sph[k], sph2[k]) for k in sph)
     del back, sph2
     torch.cuda.empty_cache()
+
+
+def test_custom_ops_match_the_methods():
+    """torch.ops.ultrasphere_b200.* launch the same kernels as the SphericalCoordinates methods."""
+    c = us.create_hopf(3)
+    h = us.plan_handle(c)
+    x = torch.rand((c.c_ndim, 50_000), device=DEV, dtype=torch.float64) * 2 - 1
+    s = c.from_cartesian(x)
+    packed = torch.ops.ultrasphere_b200.from_cartesian([x[i] for i in range(c.c_ndim)], h)
+    assert torch.equal(packed[0], s["r"])
+    for i, node in enumerate(c.s_nodes):
+        assert torch.equal(packed[1 + i], s[node])
+    back = torch.ops.ultrasphere_b200.to_cartesian([s[node] for node in c.s_nodes], s["r"], h)
+    assert torch.equal(back, c.to_cartesian(s, as_array=True))
+    no_r = torch.ops.ultrasphere_b200.to_cartesian([s[node] for node in c.s_nodes], None, h)
+    assert torch.equal(no_r, c.to_cartesian({k: v for k, v in s.items() if k != "r"}, as_array=True))
+    val = torch.rand((6, 7, 3), device=DEV, dtype=torch.float64)
+    w = [torch.rand(6, device=DEV, dtype=torch.float64), torch.rand(7, device=DEV, dtype=torch.float64)]
+    assert torch.equal(torch.ops.ultrasphere_b200.weighted_reduce(val, w), us.weighted_reduce(val, w))
+    torch.library.opcheck(torch.ops.ultrasphere_b200.from_cartesian.default, ([x[i] for i in range(c.c_ndim)], h), test_utils=("test_schema", "test_faketensor"))

@@ -197,3 +197,24 @@ def test_launch_geometry_masks():
     ops = [torch.zeros((1,) * i + (2,) + (1,) * (k - i - 1)) for i in range(k)]
     geo = _Geometry(ops, (2,) * k)
     assert geo.shape == [2**k] and all(m == 1 for m in geo.masks)
+
+
+def test_custom_ops_trace_without_a_gpu():
+    """torch.ops.ultrasphere_b200.* carry fake (shape-inferring) implementations, so FX /
+    torch.compile tracing works on any host; the real implementations exist for CUDA only."""
+    from torch._subclasses.fake_tensor import FakeTensorMode
+
+    c = us.create_standard(3)
+    h = us.plan_handle(c)
+    assert us.plan_handle(c) == h and us.plan_handle(us.create_standard(3)) != h
+    with FakeTensorMode():
+        ang = [torch.empty(5, 1, device="cuda"), torch.empty(1, 7, device="cuda"), torch.empty(5, 7, device="cuda", dtype=torch.float64)]
+        out = torch.ops.ultrasphere_b200.to_cartesian(ang, None, h)
+        assert out.shape == (4, 5, 7) and out.dtype == torch.float64
+        s = torch.ops.ultrasphere_b200.from_cartesian([torch.empty(9, device="cuda") for _ in range(4)], h)
+        assert s.shape == (4, 9) and s.dtype == torch.float32
+        v = torch.empty(4, 5, 3, device="cuda", dtype=torch.complex128)
+        w = [torch.empty(4, device="cuda", dtype=torch.float64), torch.empty(5, device="cuda", dtype=torch.float64)]
+        assert torch.ops.ultrasphere_b200.weighted_reduce(v, w).shape == (3,)
+    with pytest.raises(NotImplementedError):
+        torch.ops.ultrasphere_b200.from_cartesian([torch.zeros(3) for _ in range(4)], h)

@@ -18,6 +18,8 @@ from ._creation import (
 )
 from ._integral import integrate, roots, separable_reduce, weighted_reduce
 from ._random import random_ball
+from . import _ops as ops  # registers torch.ops.ultrasphere_b200.*
+from ._ops import plan_handle
 
 __version__ = "0.1.0"
 
@@ -34,6 +36,8 @@ __all__ = [
     "get_child",
     "get_parent",
     "integrate",
+    "ops",
+    "plan_handle",
     "random_ball",
     "roots",
     "separable_reduce",
