@@ -391,3 +391,22 @@ def test_custom_ops_match_the_methods():
     w = [torch.rand(6, device=DEV, dtype=torch.float64), torch.rand(7, device=DEV, dtype=torch.float64)]
     assert torch.equal(torch.ops.ultrasphere_b200.weighted_reduce(val, w), us.weighted_reduce(val, w))
     torch.library.opcheck(torch.ops.ultrasphere_b200.from_cartesian.default, ([x[i] for i in range(c.c_ndim)], h), test_utils=("test_schema", "test_faketensor"))
+
+
+@pytest.mark.parametrize("spec,tdt", [("standard:9", torch.float32), ("hopf:3", torch.float32), ("hopf:3", torch.float64), ("random:6:3", torch.float64)])
+def test_tiled_and_strided_paths_give_identical_bits(spec, tdt):
+    """Large batches run the TMA-tiled kernels, small ones the strided kernels; both must produce
+    the same bits (same device math, no FMA contraction in the norm chains of either)."""
+    c = make(us, spec)
+    n = 1 << 20
+    x = torch.rand((c.c_ndim, n), device=DEV, dtype=tdt) * 2 - 1
+    whole = c.from_cartesian(x)
+    back_whole = c.to_cartesian(whole, as_array=True)
+    step = 4099  # far below the tile threshold and not a multiple of the vector width
+    for lo in range(0, n, step * 37):
+        hi = min(n, lo + step)
+        part = c.from_cartesian(x[:, lo:hi].contiguous())
+        for k in whole:
+            assert torch.equal(part[k], whole[k][lo:hi]), (spec, k, lo)
+        back = c.to_cartesian({k: v[lo:hi].contiguous() for k, v in whole.items()}, as_array=True)
+        assert torch.equal(back, back_whole[:, lo:hi])

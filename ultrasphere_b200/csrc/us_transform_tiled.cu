@@ -196,11 +196,8 @@ __global__ void __launch_bounds__(kBlockThreads, 2) to_cartesian_tiled(const __g
       const Vec<T, V> th_next = lds_vec<T, V>(stage + (size_t)node_slot(w_next) * P, tid);
       Vec<T, V> pc, ps, sn, cs;
       sincos_vec<V>(th.v, sn.v, cs.v);
-#pragma unroll
-      for (int v = 0; v < V; ++v) {
-        pc.v[v] = mul_rn(cur.v[v], cs.v[v]);
-        ps.v[v] = mul_rn(cur.v[v], sn.v[v]);
-      }
+      mul_vec<V>(cur.v, cs.v, pc.v);
+      mul_vec<V>(cur.v, sn.v, ps.v);
       // data-flow form of the four node kinds (all predicates are warp-uniform):
       //   a : both products are leaves, resume the most recently deferred branch
       //   b : cos product is a leaf, continue along sin      b': sin product is a leaf, continue along cos
@@ -255,11 +252,7 @@ __global__ void __launch_bounds__(kBlockThreads, 2) from_cartesian_tiled(const _
       Vec<T, V> acc;
       for (int l = 0; l < n_rows; ++l) {
         const Vec<T, V> x = lds_vec<T, V>(stage + (size_t)l * P, tid);
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-          const T sq = mul_rn(x.v[v], x.v[v]);
-          acc.v[v] = (l == 0) ? sq : add_rn(acc.v[v], sq);
-        }
+        sumsq_step<V>(acc.v, x.v, l == 0);
       }
       sqrt_vec<V>(acc.v);
       stg_vec<T, V>(r_out + g, acc);
