@@ -66,7 +66,8 @@ class ClockSampler:
 
     def __init__(self, index: int) -> None:
         self.index = index
-        self.samples: list[tuple[float, float, int]] = []
+        self.samples: list[tuple[float, float, int, float]] = []  # (MHz, W, reason mask, host time)
+        self.window: tuple[float, float] | None = None
         self.max_mhz: float | None = None
         self._stop = threading.Event()
         self._thread: threading.Thread | None = None
@@ -98,10 +99,10 @@ class ClockSampler:
                             mask = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
                         except Exception:
                             mask = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
-                        self.samples.append((mhz, watts, mask))
+                        self.samples.append((mhz, watts, mask, time.perf_counter()))
                     except Exception:
                         pass
-                    time.sleep(0.002)
+                    time.sleep(0.001)
 
             self._mode = "nvml"
         except Exception:
@@ -120,7 +121,7 @@ class ClockSampler:
                 for line in proc.stdout:
                     cells = [c.strip() for c in line.split(",")]
                     try:
-                        self.samples.append((float(cells[0]), float(cells[2]), 0))
+                        self.samples.append((float(cells[0]), float(cells[2]), 0, time.perf_counter()))
                         self.max_mhz = float(cells[1])
                     except (ValueError, IndexError):
                         continue
@@ -137,14 +138,22 @@ class ClockSampler:
             self._thread.join(timeout=2)
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples"], "source": self._mode}
-        peak_w = max(w for _, w, _ in self.samples)
-        hot = sorted(m for m, w, _ in self.samples if w >= 0.5 * peak_w) or sorted(m for m, _, _ in self.samples)
+        # samples inside the timed region; the sampler also runs through the warm-up steps (same
+        # kernels, same load), which are used only if the timed region was too short to be sampled
+        picked = self.samples
+        scope = "warm-up + timed region"
+        if self.window is not None:
+            inside = [x for x in self.samples if self.window[0] <= x[3] <= self.window[1]]
+            if len(inside) >= 3:
+                picked, scope = inside, "timed region"
+        peak_w = max(w for _, w, _, _ in picked)
+        hot = sorted(m for m, w, _, _ in picked if w >= 0.5 * peak_w) or sorted(m for m, _, _, _ in picked)
         mask = 0
-        for _, _, m in self.samples:
+        for _, _, m, _ in picked:
             mask |= m
         return {
-            "sm_mhz": hot[len(hot) // 2], "sm_max_mhz": self.max_mhz, "power_w_max": peak_w, "samples": len(self.samples),
-            "reasons": [name for name, bit in self.REASONS if mask & bit], "source": self._mode,
+            "sm_mhz": hot[len(hot) // 2], "sm_max_mhz": self.max_mhz, "power_w_max": peak_w, "samples": len(picked),
+            "scope": scope, "reasons": [name for name, bit in self.REASONS if mask & bit], "source": self._mode,
         }
 
 
@@ -252,6 +261,9 @@ def run_b200(args: argparse.Namespace) -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     sph = None
     for _ in range(max(args.warmup, 3)):
         sph = c.from_cartesian(x)
@@ -262,10 +274,8 @@ def run_b200(args: argparse.Namespace) -> None:
         raise SystemExit(f"bench.py: round-trip error {err} exceeds 8 eps — refusing to report a number")
     del back
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    sampler = ClockSampler(local)
     barrier()
-    if rank == 0:
-        sampler.start()
+    host_t0 = time.perf_counter()
     t_begin = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
     t_begin.record()
@@ -277,6 +287,7 @@ def run_b200(args: argparse.Namespace) -> None:
         ev[k][2].record()
     t_end.record()
     barrier()
+    sampler.window = (host_t0, time.perf_counter())
     clocks = sampler.stop() if rank == 0 else None
     total_ms = t_begin.elapsed_time(t_end)
     from_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
