@@ -225,7 +225,11 @@ __global__ void __launch_bounds__(kBlockThreads, 2) to_cartesian_tiled(const __g
 // =================================================================================================
 // from_cartesian
 // =================================================================================================
-template <typename T, int V, bool STACK>
+// CHAIN: 0 = any tree (node kinds decoded per node); 1 = `b...ba` (create_standard), 2 = `b'...b'a`
+// (create_standard_prime): every node but the last has one leaf operand and the running norm as the
+// other, so the walk needs no kind switch, no operand selection, and the atan2 can skip the sign
+// logic of the operand that is known to be a norm.
+template <typename T, int V, bool STACK, int CHAIN>
 __global__ void __launch_bounds__(kBlockThreads, 2) from_cartesian_tiled(const __grid_constant__ XformParams p, int64_t n_tiles) {
   constexpr int P = kTileThreads * V;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -257,30 +261,56 @@ __global__ void __launch_bounds__(kBlockThreads, 2) from_cartesian_tiled(const _
       sqrt_vec<V>(acc.v);
       stg_vec<T, V>(r_out + g, acc);
     }
-    Vec<T, V> stack[STACK ? US_MAX_STACK : 1];
-    int sp = 0;
     Vec<T, V> cur;
-#pragma unroll
-    for (int v = 0; v < V; ++v) cur.v[v] = T(0);
+    if constexpr (CHAIN != 0) {
+      {
+        const uint64_t w = p.plan.node[nn - 1];  // the closing `a` node: two leaves
+        const Vec<T, V> vc = lds_vec<T, V>(stage + (size_t)node_cos_leaf(w) * P, tid);
+        const Vec<T, V> vs = lds_vec<T, V>(stage + (size_t)node_sin_leaf(w) * P, tid);
+        Vec<T, V> th;
+        node_from_vec<V>(vs.v, vc.v, th.v, cur.v);
+        T* o = (T*)p.out[node_slot(w)];
+        if (o) stg_vec<T, V>(o + g, th);
+      }
 #pragma unroll 2
-    for (int k = nn - 1; k >= 0; --k) {
-      const uint64_t w = p.plan.node[k];
-      const int kind = node_kind(w);
-      // operands: a leaf comes from the tile, an internal child is the running norm (`cur`) or,
-      // for the sin child of a `c` node, the norm deferred on the stack
-      if constexpr (STACK) {
-        if (kind == US_NODE_A && k != nn - 1) stack[sp++] = cur;  // finished sibling subtree waits for its `c` parent
+      for (int k = nn - 2; k >= 0; --k) {
+        const uint64_t w = p.plan.node[k];
+        const int leaf_row = (CHAIN == 1) ? node_cos_leaf(w) : node_sin_leaf(w);
+        const Vec<T, V> leaf = lds_vec<T, V>(stage + (size_t)leaf_row * P, tid);
+        Vec<T, V> th, nxt;
+        if constexpr (CHAIN == 1)
+          node_from_vec<V, true, false>(cur.v, leaf.v, th.v, nxt.v);  // theta = atan2(norm, leaf)
+        else
+          node_from_vec<V, false, true>(leaf.v, cur.v, th.v, nxt.v);  // theta = atan2(leaf, norm)
+        cur = nxt;
+        T* o = (T*)p.out[node_slot(w)];
+        if (o) stg_vec<T, V>(o + g, th);
       }
-      Vec<T, V> vc = cur, vs = cur;
-      if (kind == US_NODE_A || kind == US_NODE_B) vc = lds_vec<T, V>(stage + (size_t)node_cos_leaf(w) * P, tid);
-      if (kind == US_NODE_A || kind == US_NODE_BP) vs = lds_vec<T, V>(stage + (size_t)node_sin_leaf(w) * P, tid);
-      if constexpr (STACK) {
-        if (kind == US_NODE_C) vs = stack[--sp];
+    } else {
+      Vec<T, V> stack[STACK ? US_MAX_STACK : 1];
+      int sp = 0;
+#pragma unroll
+      for (int v = 0; v < V; ++v) cur.v[v] = T(0);
+#pragma unroll 2
+      for (int k = nn - 1; k >= 0; --k) {
+        const uint64_t w = p.plan.node[k];
+        const int kind = node_kind(w);
+        // operands: a leaf comes from the tile, an internal child is the running norm (`cur`) or,
+        // for the sin child of a `c` node, the norm deferred on the stack
+        if constexpr (STACK) {
+          if (kind == US_NODE_A && k != nn - 1) stack[sp++] = cur;  // finished sibling subtree waits for its `c` parent
+        }
+        Vec<T, V> vc = cur, vs = cur;
+        if (kind == US_NODE_A || kind == US_NODE_B) vc = lds_vec<T, V>(stage + (size_t)node_cos_leaf(w) * P, tid);
+        if (kind == US_NODE_A || kind == US_NODE_BP) vs = lds_vec<T, V>(stage + (size_t)node_sin_leaf(w) * P, tid);
+        if constexpr (STACK) {
+          if (kind == US_NODE_C) vs = stack[--sp];
+        }
+        Vec<T, V> th;
+        node_from_vec<V>(vs.v, vc.v, th.v, cur.v);
+        T* o = (T*)p.out[node_slot(w)];
+        if (o) stg_vec<T, V>(o + g, th);
       }
-      Vec<T, V> th;
-      node_from_vec<V>(vs.v, vc.v, th.v, cur.v);
-      T* o = (T*)p.out[node_slot(w)];
-      if (o) stg_vec<T, V>(o + g, th);
     }
     release_stage(sh, s);
   }
@@ -296,27 +326,35 @@ struct Variant {
   int v;
 };
 
-template <typename T, int V, bool STACK>
-static const void* to_fn() {
-  return (const void*)&to_cartesian_tiled<T, V, STACK>;
-}
-template <typename T, int V, bool STACK>
-static const void* from_fn() {
-  return (const void*)&from_cartesian_tiled<T, V, STACK>;
+template <typename T, int V>
+static const void* variant(bool to, bool stack, int chain) {
+  if (to) return stack ? (const void*)&to_cartesian_tiled<T, V, true> : (const void*)&to_cartesian_tiled<T, V, false>;
+  if (stack) return (const void*)&from_cartesian_tiled<T, V, true, 0>;
+  if (chain == 1) return (const void*)&from_cartesian_tiled<T, V, false, 1>;
+  if (chain == 2) return (const void*)&from_cartesian_tiled<T, V, false, 2>;
+  return (const void*)&from_cartesian_tiled<T, V, false, 0>;
 }
 
 template <bool TO>
-static const void* pick(int dtype, int v, bool stack) {
-#define US_PICK(T, V)                                                                      \
-  return stack ? (TO ? to_fn<T, V, true>() : from_fn<T, V, true>()) : (TO ? to_fn<T, V, false>() : from_fn<T, V, false>())
+static const void* pick(int dtype, int v, bool stack, int chain) {
   if (dtype == US_F32) {
-    if (v == 4) { US_PICK(float, 4); }
-    if (v == 2) { US_PICK(float, 2); }
-    US_PICK(float, 1);
+    if (v == 4) return variant<float, 4>(TO, stack, chain);
+    if (v == 2) return variant<float, 2>(TO, stack, chain);
+    return variant<float, 1>(TO, stack, chain);
   }
-  if (v == 2) { US_PICK(double, 2); }
-  US_PICK(double, 1);
-#undef US_PICK
+  if (v == 2) return variant<double, 2>(TO, stack, chain);
+  return variant<double, 1>(TO, stack, chain);
+}
+
+// 1: every node but the last is `b` and the last is `a`; 2: same with `b'`; 0: anything else
+static int chain_kind(const us_plan_t& plan) {
+  const int nn = plan.n_nodes;
+  if (nn < 2 || plan.max_stack != 0 || node_kind(plan.node[nn - 1]) != US_NODE_A) return 0;
+  const int first = node_kind(plan.node[0]);
+  if (first != US_NODE_B && first != US_NODE_BP) return 0;
+  for (int k = 1; k < nn - 1; ++k)
+    if (node_kind(plan.node[k]) != first) return 0;
+  return first == US_NODE_B ? 1 : 2;
 }
 
 static int sm_count() {
@@ -392,7 +430,7 @@ static int try_tiled(const XformParams& p, int dtype, cudaStream_t st) {
   const int P = kTileThreads * v;
   const int64_t n_tiles = p.n / P;
   if (n_tiles < 2 * sm_count()) return kNotTaken;  // small batches: the strided kernel is launch-bound anyway
-  const void* fn = pick<TO>(dtype, v, p.plan.max_stack > 0);
+  const void* fn = pick<TO>(dtype, v, p.plan.max_stack > 0, chain_kind(p.plan));
   const size_t smem = (size_t)kStages * n_rows * P * esz + sizeof(TileShared);
   int per_sm = 0;
   if (int rc = resident_ctas(fn, smem, &per_sm)) return rc;
