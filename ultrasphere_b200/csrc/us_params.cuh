@@ -35,4 +35,10 @@ constexpr int kNotTaken = -1000;
 int try_launch_to_cartesian_tiled(const XformParams& p, int dtype, cudaStream_t st);
 int try_launch_from_cartesian_tiled(const XformParams& p, int dtype, cudaStream_t st);
 
+// wide trees: row-ring kernels (us_transform_ring.cu); *points_per_tile = points each tile covered
+template <bool TO>
+int launch_ring(const XformParams& p, int dtype, cudaStream_t st, int* points_per_tile);
+// cached cudaFuncSetAttribute(max dynamic smem) + occupancy query
+int resident_ctas(const void* fn, size_t smem, int block_threads, int* per_sm);
+
 }  // namespace us

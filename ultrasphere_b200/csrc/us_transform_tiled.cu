@@ -21,6 +21,7 @@
 
 #include "us_common.cuh"
 #include "us_params.cuh"
+#include "us_tma.cuh"
 
 namespace us {
 
@@ -30,74 +31,6 @@ constexpr int kStages = 2;
 // 228 KB of shared memory per SM, 1 KB reserved per CTA: two CTAs of two stages each
 constexpr int kMaxStageBytes = 55 * 1024;
 constexpr int kSmemCeiling = 2 * kMaxStageBytes + 1024;
-
-// ---- PTX wrappers: mbarrier + TMA bulk copy -----------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_mbar_init() {
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {
-  }
-}
-// global -> shared bulk copy through the TMA unit; bytes % 16 == 0, both addresses 16-byte aligned
-__device__ __forceinline__ void tma_load_row(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-          smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
-      : "memory");
-}
-__device__ __forceinline__ uint64_t policy_evict_first() {
-  uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-
-// ---- V-wide register tiles ------------------------------------------------------------------
-template <typename T, int V>
-struct alignas(sizeof(T) * V) Vec {
-  T v[V];
-};
-
-template <typename T, int V>
-__device__ __forceinline__ Vec<T, V> lds_vec(const T* row, int tid) {
-  return *reinterpret_cast<const Vec<T, V>*>(row + tid * V);
-}
-
-template <typename T, int V>
-__device__ __forceinline__ void stg_vec(T* dst, const Vec<T, V>& x) {
-  if constexpr (sizeof(T) * V == 16) {
-    const float4 f = *reinterpret_cast<const float4*>(&x);
-    __stcs(reinterpret_cast<float4*>(dst), f);
-  } else if constexpr (sizeof(T) * V == 8) {
-    const float2 f = *reinterpret_cast<const float2*>(&x);
-    __stcs(reinterpret_cast<float2*>(dst), f);
-  } else {
-    __stcs(reinterpret_cast<float*>(dst), *reinterpret_cast<const float*>(&x));
-  }
-}
 
 // Issue the copies of one tile (one elected thread: UBLKCP takes uniform operands, so spreading
 // the rows over lanes would only serialise them again): post the expected byte count, then one
@@ -369,7 +302,7 @@ static int sm_count() {
 
 // cudaFuncSetAttribute + the occupancy query cost a few microseconds each; their result only
 // depends on (kernel, dynamic shared memory, device), so it is computed once and remembered.
-static int resident_ctas(const void* fn, size_t smem, int* per_sm) {
+int resident_ctas(const void* fn, size_t smem, int block_threads, int* per_sm) {
   struct Entry {
     const void* fn;
     size_t smem;
@@ -392,7 +325,7 @@ static int resident_ctas(const void* fn, size_t smem, int* per_sm) {
     if (cache[i].fn == fn && cache[i].dev == dev && cache[i].smem > ceiling) ceiling = cache[i].smem;
   if (smem > ceiling)
     US_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(smem)");
-  US_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, fn, kBlockThreads, smem), "occupancy query");
+  US_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, fn, block_threads, smem), "occupancy query");
   if (used < 128) {
     cache[used++] = Entry{fn, smem, dev, *per_sm};
   } else {
@@ -426,14 +359,21 @@ static int try_tiled(const XformParams& p, int dtype, cudaStream_t st) {
     }
     if (forced_v > 0 && forced_v <= 16 / esz) v = forced_v;
   }
-  if (v < 1) return kNotTaken;
-  const int P = kTileThreads * v;
-  const int64_t n_tiles = p.n / P;
+  int P = kTileThreads * v;
+  int64_t n_tiles = v >= 1 ? p.n / P : 0;
+  if (v < 16 / esz) {
+    // wide tree: full-width vectors through the row ring instead of narrower resident tiles
+    const int ring_p = kTileThreads * (16 / esz);
+    if (p.n / ring_p < 2 * sm_count()) return kNotTaken;
+    const int rc = launch_ring<TO>(p, dtype, st, &P);
+    if (rc != 0) return rc;
+    n_tiles = p.n / P;
+  } else {
   if (n_tiles < 2 * sm_count()) return kNotTaken;  // small batches: the strided kernel is launch-bound anyway
   const void* fn = pick<TO>(dtype, v, p.plan.max_stack > 0, chain_kind(p.plan));
   const size_t smem = (size_t)kStages * n_rows * P * esz + sizeof(TileShared);
   int per_sm = 0;
-  if (int rc = resident_ctas(fn, smem, &per_sm)) return rc;
+  if (int rc = resident_ctas(fn, smem, kBlockThreads, &per_sm)) return rc;
   if (per_sm < 1) return kNotTaken;
   int64_t grid = (int64_t)sm_count() * per_sm;
   if (grid > n_tiles) grid = n_tiles;
@@ -441,6 +381,7 @@ static int try_tiled(const XformParams& p, int dtype, cudaStream_t st) {
   int64_t tiles = n_tiles;
   void* args[] = {(void*)&body, (void*)&tiles};
   US_CUDA_TRY(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(kBlockThreads), args, smem, st), "tiled launch");
+  }
   // ragged tail (< one tile): the strided kernel on the remaining points
   const int64_t done = n_tiles * P;
   const int64_t rest = p.n - done;
