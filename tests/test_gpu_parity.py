@@ -410,3 +410,24 @@ def test_tiled_and_strided_paths_give_identical_bits(spec, tdt):
             assert torch.equal(part[k], whole[k][lo:hi]), (spec, k, lo)
         back = c.to_cartesian({k: v[lo:hi].contiguous() for k, v in whole.items()}, as_array=True)
         assert torch.equal(back, back_whole[:, lo:hi])
+
+
+@pytest.mark.parametrize("dname,ndt,tdt", DTYPES)
+@pytest.mark.parametrize("spec", ["standard:9", "standard_prime:8", "hopf:3", "random:32:0"])
+def test_tiled_ring_and_ragged_tail_against_oracle(spec, dname, ndt, tdt):
+    """Batch sizes that run the tile / chain / ring kernels plus a ragged tail (< 1 tile) handled by
+    the strided kernel, and an odd size whose rows are not 16-byte aligned (strided throughout)."""
+    c, t = make(us, spec), vo.make(spec)
+    rng = np.random.default_rng(17)
+    for n in ((1 << 20) + 772, (1 << 19) + 1):
+        x = rng.uniform(-1, 1, (c.c_ndim, n)).astype(ndt)
+        want = vo.from_cartesian(t, x)
+        got = c.from_cartesian(dev(x))
+        assert np.array_equal(host(got["r"]), want["r"]), (spec, n)
+        for k in c.s_nodes:
+            assert_angles_close(host(got[k]), want[k], f"{spec} n={n} {k}")
+        back = host(c.to_cartesian({k: dev(v) for k, v in want.items()}, as_array=True))
+        assert_leaves_close(back, vo.to_cartesian(t, want, as_array=True), want["r"], depth_of(c), f"{spec} n={n}")
+        no_r = host(c.to_cartesian({k: dev(want[k]) for k in c.s_nodes}, as_array=True))
+        wanted = vo.to_cartesian(t, {k: want[k] for k in c.s_nodes}, as_array=True)
+        assert_leaves_close(no_r, wanted, np.ones(1, ndt), depth_of(c), f"{spec} n={n} no r")
