@@ -189,7 +189,7 @@ def cpu_baseline_single_core(sample: int) -> dict:
     }
 
 
-def run_reference(args: argparse.Namespace) -> None:
+def run_reference(args: argparse.Namespace, emit) -> None:
     """The reference's CPU algorithm (NumPy port) on every host core: the batch is cut into one
     slice per thread (NumPy releases the GIL inside ufuncs)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -219,7 +219,7 @@ def run_reference(args: argparse.Namespace) -> None:
         dt = time.perf_counter() - t0
     value = sample * args.steps / dt
     desc = f"{sample} points per step split over {len(parts)} threads"
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference",
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -235,7 +235,7 @@ def run_reference(args: argparse.Namespace) -> None:
 # ----------------------------------------------------------------------------------------------
 # B200 arm
 # ----------------------------------------------------------------------------------------------
-def run_b200(args: argparse.Namespace) -> None:
+def run_b200(args: argparse.Namespace, emit) -> None:
     import torch
     import torch.distributed as dist
 
@@ -381,17 +381,33 @@ def run_b200(args: argparse.Namespace) -> None:
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_single_core(min(CPU_SAMPLE, n))
-    print(json.dumps(line))
+    emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
 def main() -> None:
     args = parse()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_b200(args)
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version
+    # banner on the first communicator), so file descriptor 1 is pointed at stderr for the whole
+    # run and the JSON line goes to the saved, real stdout at the very end.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    lines: list[str] = []
+    emit = lines.append
+    try:
+        if args.impl == "reference":
+            run_reference(args, emit)
+        else:
+            run_b200(args, emit)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    for line in lines:
+        sys.stdout.write(line + "\n")
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":

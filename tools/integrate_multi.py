@@ -22,6 +22,7 @@ from oracle import vks_oracle as vo  # noqa: E402
 
 
 def main() -> None:
+    os.environ.setdefault("NCCL_DEBUG", "WARN")  # no version banner on stdout
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
