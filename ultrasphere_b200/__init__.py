@@ -1,45 +1,33 @@
 """ultrasphere_b200 — the B200-native hot path of ultrasphere.
 
-Drop-in for the reference's transform and quadrature surface
-(/root/reference/src/ultrasphere/__init__.py:2-15): the ``create_*`` factories,
-``SphericalCoordinates`` with ``to_cartesian`` / ``from_cartesian``, ``roots`` and ``integrate``
-(``xp=torch``).  All array work runs in hand-written sm_100a CUDA kernels behind the C ABI in
-``include/ultrasphere_b200.h``; there is no CPU fallback.
+Drop-in for the reference's transform and quadrature surface: the ``create_*`` factories,
+``SphericalCoordinates`` with ``to_cartesian`` / ``from_cartesian``, ``roots``, ``integrate`` and
+``random_ball`` (``xp=torch``).  All array work runs in hand-written sm_100a CUDA kernels behind the
+C ABI in ``include/ultrasphere_b200.h``; there is no CPU fallback.
 """
-from ._coordinates import BranchingType, SphericalCoordinates, get_child, get_parent
-from ._creation import (
-    create_from_branching_types,
-    create_hopf,
-    create_polar,
-    create_random,
-    create_spherical,
-    create_standard,
-    create_standard_prime,
-)
-from ._integral import integrate, roots, separable_reduce, weighted_reduce
-from ._random import random_ball
-from . import _ops as ops  # registers torch.ops.ultrasphere_b200.*
-from ._ops import plan_handle
+from . import _coordinates as _co, _creation as _cr, _integral as _in, _ops as ops, _random as _ra
 
 __version__ = "0.1.0"
 
-__all__ = [
-    "BranchingType",
-    "SphericalCoordinates",
-    "create_from_branching_types",
-    "create_hopf",
-    "create_polar",
-    "create_random",
-    "create_spherical",
-    "create_standard",
-    "create_standard_prime",
-    "get_child",
-    "get_parent",
-    "integrate",
-    "ops",
-    "plan_handle",
-    "random_ball",
-    "roots",
-    "separable_reduce",
-    "weighted_reduce",
-]
+# coordinate object and tree helpers
+BranchingType, SphericalCoordinates = _co.BranchingType, _co.SphericalCoordinates
+get_child, get_parent = _co.get_child, _co.get_parent
+# factories
+create_polar, create_spherical = _cr.create_polar, _cr.create_spherical
+create_standard, create_standard_prime = _cr.create_standard, _cr.create_standard_prime
+create_hopf, create_random = _cr.create_hopf, _cr.create_random
+create_from_branching_types = _cr.create_from_branching_types
+# quadrature, sampling, fused reductions
+roots, integrate = _in.roots, _in.integrate
+weighted_reduce, separable_reduce = _in.weighted_reduce, _in.separable_reduce
+random_ball = _ra.random_ball
+# torch.ops.ultrasphere_b200.* (registered by importing `ops`)
+plan_handle = ops.plan_handle
+
+__all__ = tuple(
+    sorted(
+        name
+        for name, value in list(globals().items())
+        if not name.startswith("_") and (callable(value) or name == "ops")
+    )
+)
