@@ -454,3 +454,23 @@ def test_cuda_graph_capture_and_replay():
         for k in eager:
             assert torch.equal(static_s[k], eager[k])
         assert torch.equal(static_y, c.to_cartesian(eager, as_array=True))
+
+
+@pytest.mark.parametrize("spec,ndt", [("standard:256", np.float64), ("hopf:8", np.float64), ("hopf:8", np.float32), ("random:200:5", np.float64)])
+def test_maximum_tree_sizes(spec, ndt):
+    """Capacity limits of the compiled plan: 256 angles (a 257-D chain, leaf depth 256), the perfect
+    binary tree with 255 angles (deferred-branch stack depth 7) and a 200-angle random tree."""
+    c, t = make(us, spec), vo.make(spec)
+    assert c.s_ndim <= 256
+    n = 2048
+    x = np.random.default_rng(23).uniform(-1, 1, (c.c_ndim, n)).astype(ndt)
+    want = vo.from_cartesian(t, x)
+    got = c.from_cartesian(dev(x))
+    assert list(got) == list(want)
+    assert np.array_equal(host(got["r"]), want["r"])
+    for k in c.s_nodes:
+        assert_angles_close(host(got[k]), want[k], f"{spec} {k}")
+    back = host(c.to_cartesian({k: dev(v) for k, v in want.items()}, as_array=True))
+    assert_leaves_close(back, vo.to_cartesian(t, want, as_array=True), want["r"], depth_of(c), spec)
+    with pytest.raises(ValueError):
+        us.create_standard(257).from_cartesian(torch.zeros((258, 4), device=DEV))
