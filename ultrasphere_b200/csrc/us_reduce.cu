@@ -10,6 +10,8 @@
 // warps) are written to caller-provided scratch and a second, single-block kernel adds them in a
 // fixed order, so the result is bit-reproducible for a given shape.
 #include "us_common.cuh"
+#include "us_params.cuh"
+#include "us_tma.cuh"
 
 namespace us {
 
@@ -186,6 +188,109 @@ __global__ void __launch_bounds__(kRedThreads) wreduce_cols(const __grid_constan
   if (live_col) p.partial[(int64_t)blockIdx.y * m64 + col] = acc;
 }
 
+// TMA-streamed rows kernel (m <= 32, the hot case: real / complex scalar integrands).  `val` is one
+// contiguous array, so a persistent CTA's producer warp streams it through a ring of shared-memory
+// slots with ONE bulk copy per slab of whole grid rows (cp.async.bulk, mbarrier completion): the
+// bytes in flight per SM are set by the ring (4 x 32 KB per CTA), not by registers or occupancy.
+// Consumer warps take the rows of a slab round-robin; a row's outer weight needs the row index
+// decomposed once per row (warp-uniform), the lanes then stride the row in shared memory.
+constexpr int kRedSlots = 4;
+constexpr int kRedSlotBytes = 24 * 1024;  // 4 slots x 24 KB (+ weights) per CTA: two CTAs per SM
+constexpr int kRedMaxRows = 256;          // rows per slab (their outer weights live next to the slot)
+
+struct RedRing {
+  uint64_t full[kRedSlots];
+  uint64_t empty[kRedSlots];
+  double wrow[kRedSlots][kRedMaxRows];  // outer weight of every row of the slab in each slot
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kRedThreads + 32, 2) wreduce_tma(const __grid_constant__ ReduceParams p, int rows_per_slab,
+                                                                     int64_t n_slabs) {
+  extern __shared__ __align__(128) unsigned char red_smem[];
+  T* ring = reinterpret_cast<T*>(red_smem);
+  RedRing* sh = reinterpret_cast<RedRing*>(red_smem + (size_t)kRedSlots * kRedSlotBytes);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kRedSlots; ++s) {
+      mbar_init(&sh->full[s], 1);
+      mbar_init(&sh->empty[s], kRedWarps);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int m = p.m, W = p.lanes;
+  const int64_t run = p.inner * m;  // contiguous values per row
+  __shared__ double sm[kRedWarps][32];
+  if (warp == kRedWarps) {
+    // producer warp: while the slot drains, its lanes compute the slab's row weights (index
+    // decomposition with divisions — off the consumers' critical path), then one lane posts the
+    // byte count and issues the slab's single bulk copy
+    const uint64_t policy = policy_evict_first();
+    uint32_t q = 0;
+    for (int64_t slab = blockIdx.x; slab < n_slabs; slab += gridDim.x, ++q) {
+      const int slot = (int)(q % kRedSlots);
+      if (q >= (uint32_t)kRedSlots) mbar_wait(&sh->empty[slot], ((q / kRedSlots) - 1u) & 1u);
+      const int64_t row0 = slab * rows_per_slab;
+      const int nrows = (int)min((int64_t)rows_per_slab, p.rows - row0);
+      for (int r = lane; r < nrows; r += 32) {
+        int64_t rem = row0 + r;
+        double wr = 1.0;
+        for (int d = p.ndim - 2; d >= 0; --d) {
+          const int64_t e = p.extent[d];
+          const int64_t qd = rem / e;
+          wr *= ldw<T>(p.w[d], rem - qd * e);
+          rem = qd;
+        }
+        sh->wrow[slot][r] = wr;
+      }
+      __syncwarp();
+      if (lane == 0) {
+        const uint32_t bytes = (uint32_t)((int64_t)nrows * run * (int64_t)sizeof(T));
+        mbar_arrive_expect_tx(&sh->full[slot], bytes);  // release: the weights above are visible to waiters
+        tma_load_row(reinterpret_cast<unsigned char*>(ring) + (size_t)slot * kRedSlotBytes, (const T*)p.val + row0 * run, bytes,
+                     &sh->full[slot], policy);
+      }
+    }
+  } else {
+    const int lw = W / m, l0 = lane / m;
+    const bool active = lane < W;
+    const void* wl = p.w[p.ndim - 1];
+    double acc = 0.0;
+    uint32_t q = 0;
+    for (int64_t slab = blockIdx.x; slab < n_slabs; slab += gridDim.x, ++q) {
+      const int slot = (int)(q % kRedSlots);
+      mbar_wait(&sh->full[slot], (q / kRedSlots) & 1u);
+      const T* base = reinterpret_cast<const T*>(reinterpret_cast<const unsigned char*>(ring) + (size_t)slot * kRedSlotBytes);
+      const int nrows = (int)min((int64_t)rows_per_slab, p.rows - slab * rows_per_slab);
+      for (int r = warp; r < nrows; r += kRedWarps) {
+        const T* row = base + (int64_t)r * run;
+        double a0 = 0.0, a1 = 0.0;
+        int64_t e = lane, l = l0;
+        for (; e + W < run; e += 2 * W, l += 2 * lw) {
+          if (active) {
+            a0 = fma(ldw<T>(wl, l), (double)row[e], a0);
+            a1 = fma(ldw<T>(wl, l + lw), (double)row[e + W], a1);
+          }
+        }
+        if (active && e < run) a0 = fma(ldw<T>(wl, l), (double)row[e], a0);
+        acc = fma(sh->wrow[slot][r], a0 + a1, acc);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh->empty[slot]);
+    }
+    sm[warp][lane] = active ? acc : 0.0;
+  }
+  __syncthreads();
+  if (tid < m) {
+    double t = 0.0;
+    for (int wv = 0; wv < kRedWarps; ++wv)
+      for (int l = tid; l < W; l += m) t += sm[wv][l];
+    p.partial[(int64_t)blockIdx.x * m + tid] = t;
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) wreduce_final(const double* __restrict__ partial, int nblocks,
                                                      int64_t m, T* __restrict__ out, int accumulate) {
@@ -292,6 +397,40 @@ extern "C" int us_weighted_reduce(int dtype, int ndim, const int64_t* extent, co
   cudaStream_t st = (cudaStream_t)stream;
   int gx, gy;
   const int nparts = reduce_blocks(m, total, p.rows, &gx, &gy);
+  int nparts_used = nparts;
+  const int esz = dtype == US_F32 ? 4 : 8;
+  const int64_t run_bytes = p.inner * m * esz;
+  if (rows_ok(m) && run_bytes <= kRedSlotBytes / 2 && total * m * esz >= (8 << 20) &&
+      (reinterpret_cast<uintptr_t>(val_dev) & 15u) == 0) {
+    // TMA-streamed path: slabs of whole rows; a slab's byte count must be a multiple of 16
+    p.m = (int32_t)m;
+    p.lanes = (int32_t)((32 / m) * m);
+    int rows_per_slab = (int)(kRedSlotBytes / run_bytes);
+    if (rows_per_slab > kRedMaxRows) rows_per_slab = kRedMaxRows;
+    while (rows_per_slab > 1 && (rows_per_slab * run_bytes) % 16 != 0) --rows_per_slab;
+    if ((rows_per_slab * run_bytes) % 16 == 0 && (p.rows % rows_per_slab == 0 || ((p.rows % rows_per_slab) * run_bytes) % 16 == 0)) {
+      const int64_t n_slabs = (p.rows + rows_per_slab - 1) / rows_per_slab;
+      int dev = 0, sms = 148;
+      US_CUDA_TRY(cudaGetDevice(&dev), "cudaGetDevice");
+      US_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute");
+      const void* fn = dtype == US_F32 ? (const void*)&wreduce_tma<float> : (const void*)&wreduce_tma<double>;
+      const size_t smem = (size_t)kRedSlots * kRedSlotBytes + sizeof(RedRing);
+      int per_sm = 0;
+      if (int rc = resident_ctas(fn, smem, kRedThreads + 32, &per_sm)) return rc;
+      if (per_sm >= 1) {
+        int64_t grid = (int64_t)sms * per_sm;
+        if (grid > n_slabs) grid = n_slabs;
+        if (grid > kMaxRedBlocks) grid = kMaxRedBlocks;
+        ReduceParams body = p;
+        int rps = rows_per_slab;
+        int64_t ns = n_slabs;
+        void* args[] = {(void*)&body, (void*)&rps, (void*)&ns};
+        US_CUDA_TRY(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(kRedThreads + 32), args, smem, st), "wreduce_tma launch");
+        nparts_used = (int)grid;
+        goto final_pass;
+      }
+    }
+  }
   if (rows_ok(m)) {
     p.m = (int32_t)m;
     p.lanes = (int32_t)((32 / m) * m);
@@ -307,11 +446,12 @@ extern "C" int us_weighted_reduce(int dtype, int ndim, const int64_t* extent, co
       wreduce_cols<double><<<grid, kRedThreads, 0, st>>>(p, total, m);
   }
   US_CUDA_TRY(cudaGetLastError(), "weighted_reduce launch");
+final_pass:
   const int fb = (int)((m + 255) / 256);
   if (dtype == US_F32)
-    wreduce_final<float><<<fb, 256, 0, st>>>(p.partial, nparts, m, (float*)out_dev, accumulate);
+    wreduce_final<float><<<fb, 256, 0, st>>>(p.partial, nparts_used, m, (float*)out_dev, accumulate);
   else
-    wreduce_final<double><<<fb, 256, 0, st>>>(p.partial, nparts, m, (double*)out_dev, accumulate);
+    wreduce_final<double><<<fb, 256, 0, st>>>(p.partial, nparts_used, m, (double*)out_dev, accumulate);
   US_CUDA_TRY(cudaGetLastError(), "weighted_reduce final launch");
   return 0;
 }
