@@ -60,11 +60,14 @@ __device__ __forceinline__ void store_vec(T* dst, const BVec<T, V>& x) {
   }
 }
 
-// One thread owns V consecutive grid points (V divides the innermost extent, so they share all
-// outer indices).  I is the index type: uint32_t whenever the grid has < 2^32 points.
-template <typename T, int V, int MAXD, typename I>
+// One thread owns U groups of V consecutive grid points (U*V divides the innermost extent, so they
+// share all outer indices: one index decomposition and, for operands that do not span the
+// innermost dim, one table look-up serve all of them).  I is the index type: uint32_t whenever the
+// grid has < 2^32 points.
+template <typename T, int V, int U, bool STACK, int MAXD, typename I>
 __global__ void __launch_bounds__(256) to_cartesian_bcast(const __grid_constant__ XformParams p) {
-  const I g0 = ((I)blockIdx.x * blockDim.x + threadIdx.x) * V;
+  constexpr int E = U * V;  // elements per thread
+  const I g0 = ((I)blockIdx.x * blockDim.x + threadIdx.x) * E;
   if (g0 >= (I)p.n) return;
   const int nd = p.ndim;
   I idx[MAXD];
@@ -95,17 +98,17 @@ __global__ void __launch_bounds__(256) to_cartesian_bcast(const __grid_constant_
     return o;
   };
   const uint32_t last_bit = 1u << (nd - 1);
-  BVec<T, V> cur;
+  T cur[E];
   if (p.r_in) {
     const I o = offset(p.r_mask);
     const I step = (p.r_mask & last_bit) ? 1 : 0;
 #pragma unroll
-    for (int v = 0; v < V; ++v) cur.v[v] = __ldg((const T*)p.r_in + o + (I)v * step);
+    for (int v = 0; v < E; ++v) cur[v] = __ldg((const T*)p.r_in + o + (I)v * step);
   } else {
 #pragma unroll
-    for (int v = 0; v < V; ++v) cur.v[v] = T(1);
+    for (int v = 0; v < E; ++v) cur[v] = T(1);
   }
-  BVec<T, V> stack[US_MAX_STACK];
+  T stack[STACK ? US_MAX_STACK : 1][E];  // chains (create_standard...) need none
   int sp = 0;
   const int nn = p.plan.n_nodes;
   for (int k = 0; k < nn; ++k) {
@@ -113,37 +116,64 @@ __global__ void __launch_bounds__(256) to_cartesian_bcast(const __grid_constant_
     const int slot = node_slot(w);
     const uint32_t mask = p.in_mask[slot];
     const I o = offset(mask);
-    const I step = (mask & last_bit) ? 1 : 0;
-    BVec<T, V> sn, cs;
+    const bool varies = (mask & last_bit) != 0;  // warp-uniform
+    T sn[E], cs[E];
     if (p.tab[slot]) {
       const typename Pair<T>::type* tb = (const typename Pair<T>::type*)p.tab[slot];
+      if (varies) {
 #pragma unroll
-      for (int v = 0; v < V; ++v) {
-        const typename Pair<T>::type sc = __ldg(tb + o + (I)v * step);
-        sn.v[v] = sc.x;
-        cs.v[v] = sc.y;
+        for (int v = 0; v < E; ++v) {
+          const typename Pair<T>::type sc = __ldg(tb + o + (I)v);
+          sn[v] = sc.x;
+          cs[v] = sc.y;
+        }
+      } else {
+        const typename Pair<T>::type sc = __ldg(tb + o);
+#pragma unroll
+        for (int v = 0; v < E; ++v) {
+          sn[v] = sc.x;
+          cs[v] = sc.y;
+        }
       }
     } else {
-      BVec<T, V> th;
+      T th[E];
 #pragma unroll
-      for (int v = 0; v < V; ++v) th.v[v] = __ldg((const T*)p.in[slot] + o + (I)v * step);
-      sincos_vec<V>(th.v, sn.v, cs.v);
+      for (int v = 0; v < E; ++v) th[v] = __ldg((const T*)p.in[slot] + o + (varies ? (I)v : (I)0));
+      sincos_vec<E>(th, sn, cs);
     }
-    BVec<T, V> pc, ps;
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-      pc.v[v] = mul_rn(cur.v[v], cs.v[v]);
-      ps.v[v] = mul_rn(cur.v[v], sn.v[v]);
-    }
+    T pc[E], ps[E];
+    mul_vec<E>(cur, cs, pc);
+    mul_vec<E>(cur, sn, ps);
     const int kind = node_kind(w);
     T* const oc = (kind == US_NODE_A || kind == US_NODE_B) ? (T*)p.out[node_cos_leaf(w)] : nullptr;
     T* const os = (kind == US_NODE_A || kind == US_NODE_BP) ? (T*)p.out[node_sin_leaf(w)] : nullptr;
-    if (kind == US_NODE_C) stack[sp++] = ps;
+    if constexpr (STACK) {
+      if (kind == US_NODE_C) {
 #pragma unroll
-    for (int v = 0; v < V; ++v) cur.v[v] = (kind == US_NODE_B) ? ps.v[v] : pc.v[v];
-    if (kind == US_NODE_A && sp > 0) cur = stack[--sp];
-    if (oc) store_vec<T, V>(oc + g0, pc);
-    if (os) store_vec<T, V>(os + g0, ps);
+        for (int v = 0; v < E; ++v) stack[sp][v] = ps[v];
+        ++sp;
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < E; ++v) cur[v] = (kind == US_NODE_B) ? ps[v] : pc[v];
+    if constexpr (STACK) {
+      if (kind == US_NODE_A && sp > 0) {
+        --sp;
+#pragma unroll
+        for (int v = 0; v < E; ++v) cur[v] = stack[sp][v];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      BVec<T, V> tc, ts;
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        tc.v[v] = pc[u * V + v];
+        ts.v[v] = ps[u * V + v];
+      }
+      if (oc) store_vec<T, V>(oc + g0 + u * V, tc);
+      if (os) store_vec<T, V>(os + g0 + u * V, ts);
+    }
   }
 }
 
@@ -172,14 +202,28 @@ int64_t bcast_workspace_bytes(const us_plan_t* plan, int dtype, int64_t n, int n
   return bytes;
 }
 
-template <typename T, int V, int MAXD>
+template <typename T, int V, int U, bool STACK, int MAXD>
 static void launch_bcast(const XformParams& p, cudaStream_t st) {
-  const int64_t threads_total = (p.n + V - 1) / V;
+  const int64_t threads_total = (p.n + V * U - 1) / (V * U);
   const unsigned blocks = (unsigned)((threads_total + 255) / 256);
-  if (p.n < (int64_t)0xFFFFFFFFLL - 1024)
-    to_cartesian_bcast<T, V, MAXD, uint32_t><<<blocks, 256, 0, st>>>(p);
+  if (p.n < (int64_t)0xFFFFFFFFLL - 4096)
+    to_cartesian_bcast<T, V, U, STACK, MAXD, uint32_t><<<blocks, 256, 0, st>>>(p);
   else
-    to_cartesian_bcast<T, V, MAXD, uint64_t><<<blocks, 256, 0, st>>>(p);
+    to_cartesian_bcast<T, V, U, STACK, MAXD, uint64_t><<<blocks, 256, 0, st>>>(p);
+}
+
+template <typename T, int MAXD>
+static void launch_bcast_shape(const XformParams& p, bool vec_ok, cudaStream_t st) {
+  constexpr int VMAX = 16 / (int)sizeof(T);
+  if (p.plan.max_stack > 0) {  // trees with `c` nodes: one vector per thread, stack in local memory
+    vec_ok ? launch_bcast<T, VMAX, 1, true, MAXD>(p, st) : launch_bcast<T, 1, 1, true, MAXD>(p, st);
+  } else if (vec_ok) {
+    // (U = 4 groups per thread was measured SLOWER: 2.39 vs 1.44 ms on C5 — each store instruction
+    // of a warp then covers 32 x 16 B at a 64 B stride instead of one contiguous 512 B segment)
+    launch_bcast<T, VMAX, 1, false, MAXD>(p, st);
+  } else {
+    launch_bcast<T, 1, 1, false, MAXD>(p, st);
+  }
 }
 
 int try_launch_to_cartesian_bcast(XformParams& p, int dtype, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
@@ -224,11 +268,9 @@ int try_launch_to_cartesian_bcast(XformParams& p, int dtype, void* workspace, in
     if (p.out[l] && (reinterpret_cast<uintptr_t>(p.out[l]) & 15u)) vec_ok = false;
   const bool small = p.ndim <= 4;
   if (dtype == US_F32) {
-    if (vec_ok) small ? launch_bcast<float, 4, 4>(p, st) : launch_bcast<float, 4, 8>(p, st);
-    else small ? launch_bcast<float, 1, 4>(p, st) : launch_bcast<float, 1, 8>(p, st);
+    small ? launch_bcast_shape<float, 4>(p, vec_ok, st) : launch_bcast_shape<float, 8>(p, vec_ok, st);
   } else {
-    if (vec_ok) small ? launch_bcast<double, 2, 4>(p, st) : launch_bcast<double, 2, 8>(p, st);
-    else small ? launch_bcast<double, 1, 4>(p, st) : launch_bcast<double, 1, 8>(p, st);
+    small ? launch_bcast_shape<double, 4>(p, vec_ok, st) : launch_bcast_shape<double, 8>(p, vec_ok, st);
   }
   US_CUDA_TRY(cudaGetLastError(), "to_cartesian_bcast launch");
   return 0;
