@@ -189,17 +189,39 @@ __global__ void __launch_bounds__(kRingBlock, 3) from_cartesian_ring(const __gri
     for (int v = 0; v < V; ++v) cur.v[v] = T(0);
     for (int k = nn - 1; k >= 0; --k) {
       const uint64_t w = p.plan.node[k];
-      const int kind = node_kind(w);
-      if (kind == US_NODE_A && k != nn - 1) stack[sp++] = cur;
-      Vec<T, V> vc = cur, vs = cur;
-      int slot_c = -1, slot_s = -1;
-      if (kind == US_NODE_A || kind == US_NODE_B) vc = ring.get(slot_c);
-      if (kind == US_NODE_A || kind == US_NODE_BP) vs = ring.get(slot_s);
-      if (kind == US_NODE_C) vs = stack[--sp];
-      Vec<T, V> th;
-      node_from_vec<V>(vs.v, vc.v, th.v, cur.v);
-      if (slot_c >= 0) ring.release(slot_c);
-      if (slot_s >= 0) ring.release(slot_s);
+      Vec<T, V> th, nxt;
+      switch (node_kind(w)) {  // one specialised body per node kind (see from_cartesian_tiled)
+        case US_NODE_A: {
+          if (k != nn - 1) stack[sp++] = cur;
+          int slot_c, slot_s;
+          const Vec<T, V> vc = ring.get(slot_c);
+          const Vec<T, V> vs = ring.get(slot_s);
+          node_from_vec<V, false, false>(vs.v, vc.v, th.v, nxt.v);
+          ring.release(slot_c);
+          ring.release(slot_s);
+          break;
+        }
+        case US_NODE_B: {
+          int slot_c;
+          const Vec<T, V> vc = ring.get(slot_c);
+          node_from_vec<V, true, false>(cur.v, vc.v, th.v, nxt.v);
+          ring.release(slot_c);
+          break;
+        }
+        case US_NODE_BP: {
+          int slot_s;
+          const Vec<T, V> vs = ring.get(slot_s);
+          node_from_vec<V, false, true>(vs.v, cur.v, th.v, nxt.v);
+          ring.release(slot_s);
+          break;
+        }
+        default: {
+          const Vec<T, V> vs = stack[--sp];
+          node_from_vec<V, true, true>(vs.v, cur.v, th.v, nxt.v);
+          break;
+        }
+      }
+      cur = nxt;
       T* o = (T*)p.out[node_slot(w)];
       if (o) stg_vec<T, V>(o + g, th);
     }

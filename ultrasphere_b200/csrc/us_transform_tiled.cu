@@ -220,27 +220,43 @@ __global__ void __launch_bounds__(kBlockThreads, 2) from_cartesian_tiled(const _
         if (o) stg_vec<T, V>(o + g, th);
       }
     } else {
+      // Any tree: one specialised body per node kind (warp-uniform switch), so that no operand has
+      // to be selected at run time and the atan2 can drop the sign logic of operands that are norms.
       Vec<T, V> stack[STACK ? US_MAX_STACK : 1];
       int sp = 0;
 #pragma unroll
       for (int v = 0; v < V; ++v) cur.v[v] = T(0);
-#pragma unroll 2
       for (int k = nn - 1; k >= 0; --k) {
         const uint64_t w = p.plan.node[k];
-        const int kind = node_kind(w);
-        // operands: a leaf comes from the tile, an internal child is the running norm (`cur`) or,
-        // for the sin child of a `c` node, the norm deferred on the stack
-        if constexpr (STACK) {
-          if (kind == US_NODE_A && k != nn - 1) stack[sp++] = cur;  // finished sibling subtree waits for its `c` parent
+        Vec<T, V> th, nxt;
+        switch (node_kind(w)) {
+          case US_NODE_A: {  // two leaves; a finished sibling subtree waits for its `c` parent
+            if constexpr (STACK) {
+              if (k != nn - 1) stack[sp++] = cur;
+            }
+            const Vec<T, V> vc = lds_vec<T, V>(stage + (size_t)node_cos_leaf(w) * P, tid);
+            const Vec<T, V> vs = lds_vec<T, V>(stage + (size_t)node_sin_leaf(w) * P, tid);
+            node_from_vec<V, false, false>(vs.v, vc.v, th.v, nxt.v);
+            break;
+          }
+          case US_NODE_B: {  // cos child leaf, sin child = running norm (>= 0)
+            const Vec<T, V> vc = lds_vec<T, V>(stage + (size_t)node_cos_leaf(w) * P, tid);
+            node_from_vec<V, true, false>(cur.v, vc.v, th.v, nxt.v);
+            break;
+          }
+          case US_NODE_BP: {  // sin child leaf, cos child = running norm (>= 0)
+            const Vec<T, V> vs = lds_vec<T, V>(stage + (size_t)node_sin_leaf(w) * P, tid);
+            node_from_vec<V, false, true>(vs.v, cur.v, th.v, nxt.v);
+            break;
+          }
+          default: {  // both children internal: cos = running norm, sin = the deferred norm
+            Vec<T, V> vs = cur;
+            if constexpr (STACK) vs = stack[--sp];
+            node_from_vec<V, true, true>(vs.v, cur.v, th.v, nxt.v);
+            break;
+          }
         }
-        Vec<T, V> vc = cur, vs = cur;
-        if (kind == US_NODE_A || kind == US_NODE_B) vc = lds_vec<T, V>(stage + (size_t)node_cos_leaf(w) * P, tid);
-        if (kind == US_NODE_A || kind == US_NODE_BP) vs = lds_vec<T, V>(stage + (size_t)node_sin_leaf(w) * P, tid);
-        if constexpr (STACK) {
-          if (kind == US_NODE_C) vs = stack[--sp];
-        }
-        Vec<T, V> th;
-        node_from_vec<V>(vs.v, vc.v, th.v, cur.v);
+        cur = nxt;
         T* o = (T*)p.out[node_slot(w)];
         if (o) stg_vec<T, V>(o + g, th);
       }
