@@ -207,3 +207,52 @@ def test_full_size_quadrature_matches_analytic():
     want = vo.analytic_exp_kx(k5)
     assert abs(got - want) <= INTEGRAL_REL * want
     assert abs(got - 29.44939782558211) <= INTEGRAL_REL * want  # the reference's own n=96 value
+
+
+@pytest.mark.parametrize("n", [1, 2, 3])
+@pytest.mark.parametrize("spec", ["polar", "spherical", "standard:3", "hopf:2"])
+def test_tiny_rules_match_oracle(spec, n):
+    """Degenerate rule sizes (n = 1 gives a 1-point Gauss rule and a 2-point trapezoid)."""
+    c, t = make(us, spec), vo.make(spec)
+    k = np.linspace(0.3, 0.9, c.c_ndim)
+    kd = torch.from_numpy(k).to(DEV)
+    want = vo.integrate(t, lambda s: np.exp(np.einsum("v,v...->...", k, vo.to_cartesian(t, s, as_array=True))), False, n)
+    got = us.integrate(
+        c, lambda s: torch.exp(torch.einsum("v,v...->...", kd, c.to_cartesian(s, as_array=True))), False, n,
+        xp=torch, device=DEV, dtype=torch.float64,
+    )
+    assert abs(got.item() - float(want)) <= INTEGRAL_REL * abs(float(want))
+    sep_w = vo.integrate(t, lambda s: {node: np.cos(s[node]) + 2 for node in t.s_nodes}, True, n)
+    sep_g = us.integrate(c, lambda s: {node: torch.cos(s[node]) + 2 for node in c.s_nodes}, True, n, xp=torch, device=DEV, dtype=torch.float64)
+    for node in c.s_nodes:
+        assert abs(sep_g[node].item() - float(sep_w[node])) <= 1e-13 * abs(float(sep_w[node]))
+
+
+def test_integrand_variants_match_oracle():
+    """Mapping given instead of a callable, float32 values under float64 rules, an integrand that
+    ignores the leading angle (size-1 leading axis), and a sliced (non-contiguous) value tensor."""
+    c, t = us.create_standard(3), vo.create_standard(3)
+    n = 7
+    xs, _ = us.roots(c, n, expand_dims_x=True, xp=torch, device=DEV, dtype=torch.float64)
+    nxs, _ = vo.roots(t, n, expand_dims_x=True)
+    # size-1 leading axis
+    got = us.integrate(c, lambda s: torch.sin(s["theta1"]) ** 2 * torch.cos(s["theta2"]) ** 2, False, n, xp=torch, device=DEV, dtype=torch.float64)
+    want = vo.integrate(t, lambda s: np.sin(s["theta1"]) ** 2 * np.cos(s["theta2"]) ** 2, False, n)
+    assert got.shape == () and abs(got.item() - float(want)) <= INTEGRAL_REL * abs(float(want))
+    # non-contiguous values: every other trailing component of a wider tensor
+    wide = torch.stack([torch.cos(xs["theta0"]) ** 2 * (1 + 0 * xs["theta1"]) * (j + 1 + 0 * xs["theta2"]) for j in range(6)], dim=-1)
+    got = us.integrate(c, wide[..., ::2], False, n, xp=torch, device=DEV, dtype=torch.float64)
+    nwide = np.stack([np.cos(nxs["theta0"]) ** 2 * (1 + 0 * nxs["theta1"]) * (j + 1 + 0 * nxs["theta2"]) for j in range(6)], axis=-1)
+    want = vo.integrate(t, nwide[..., ::2], False, n)
+    np.testing.assert_allclose(host(got), want, rtol=INTEGRAL_REL)
+    # float32 values with float64 rules promote to float64
+    got = us.integrate(c, lambda s: (torch.cos(s["theta0"]) ** 2 + 0 * s["theta1"] + 0 * s["theta2"]).float(), False, n, xp=torch, device=DEV, dtype=torch.float64)
+    assert got.dtype == torch.float64
+    # separable mapping passed directly
+    xs1, _ = us.roots(c, n, expand_dims_x=False, xp=torch, device=DEV, dtype=torch.float64)
+    given = {node: torch.cos(xs1[node]) ** 2 for node in c.s_nodes}
+    sep = us.integrate(c, given, True, n, xp=torch, device=DEV, dtype=torch.float64)
+    nxs1, _ = vo.roots(t, n, expand_dims_x=False)
+    wsep = vo.integrate(t, {node: np.cos(nxs1[node]) ** 2 for node in t.s_nodes}, True, n)
+    for node in c.s_nodes:
+        assert abs(sep[node].item() - float(wsep[node])) <= 1e-13 * max(1.0, abs(float(wsep[node])))
