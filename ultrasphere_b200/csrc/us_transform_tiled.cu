@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(kBlockThreads, 2) to_cartesian_tiled(const __g
 // other, so the walk needs no kind switch, no operand selection, and the atan2 can skip the sign
 // logic of the operand that is known to be a norm.
 template <typename T, int V, bool STACK, int CHAIN>
-__global__ void __launch_bounds__(kBlockThreads, 2) from_cartesian_tiled(const __grid_constant__ XformParams p, int64_t n_tiles) {
+__global__ void __launch_bounds__(kBlockThreads, sizeof(T) == 8 ? 3 : 2) from_cartesian_tiled(const __grid_constant__ XformParams p, int64_t n_tiles) {
   constexpr int P = kTileThreads * V;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int nn = p.plan.n_nodes;
