@@ -174,6 +174,20 @@ US_API int us_separable_reduce(int dtype, int n_axes, const int64_t* len, const 
                         void* const* out_dev, void* stream);
 
 /*
+ * ---- "next" row: SphericalCoordinates.jacobian (_coordinates.py:668-702) ----
+ * out = r * prod over internal nodes of cos(theta)^cos_pow * sin(theta)^sin_pow, one fused pass that
+ * shares the sincos with nothing else to write: (s_ndim + 2) * sizeof(T) bytes per point.  The
+ * exponents are S[child] + 1 for an internal child and 0 for a leaf (the reference reads NaN for
+ * leaves and therefore returns NaN for every tree; this is the formula it intends).  Operands are
+ * addressed exactly as in us_to_cartesian (launch shape + per-operand masks); r_dev may be NULL.
+ * cos_pow / sin_pow: n_nodes entries in s_nodes order.
+ */
+US_API int us_jacobian(const us_plan_t* plan, int dtype, int64_t n, int ndim, const int64_t* shape,
+                       const void* const* angle_dev, const uint32_t* angle_mask, const void* r_dev,
+                       uint32_t r_mask, const int32_t* cos_pow, const int32_t* sin_pow, void* out_dev,
+                       void* stream);
+
+/*
  * ---- "next" row of the path: the producer of transform inputs ----
  * Uniform points in the unit ball (surface = 0) or on the unit sphere (surface = 1) of dimension
  * `dim`, written as `dim` arrays of n elements (reference: src/ultrasphere/_random.py:16-57, which

@@ -474,3 +474,45 @@ def test_maximum_tree_sizes(spec, ndt):
     assert_leaves_close(back, vo.to_cartesian(t, want, as_array=True), want["r"], depth_of(c), spec)
     with pytest.raises(ValueError):
         us.create_standard(257).from_cartesian(torch.zeros((258, 4), device=DEV))
+
+
+@pytest.mark.parametrize("spec", ["spherical", "standard:4", "hopf:3", "expr:cbabba", "random:32:0"])
+def test_jacobian_is_the_intended_formula(spec):
+    """SURVEY.md §8f-3: the reference's jacobian() is NaN for every tree (leaf entries of S are NaN);
+    ours implements the formula it intends.  Checked against a float64 NumPy evaluation and, for the
+    standard tree, against the textbook sin-power form and the sphere's area."""
+    c, t = make(us, spec), vo.make(spec)
+    rng = np.random.default_rng(31)
+    n = 5000
+    ang = {k: rng.uniform(0.1, 1.4, n) for k in c.s_nodes}
+    rr = rng.uniform(0.5, 2.0, n)
+    want = rr.copy()
+    for node in t.s_nodes:
+        for kind, fn in (("cos", np.cos), ("sin", np.sin)):
+            child = t.child(node, kind)
+            power = 0 if not t.adj[child] else int(t.S[child]) + 1
+            want = want * fn(ang[node]) ** power
+    got = c.jacobian({k: dev(v) for k, v in ang.items()} | {"r": dev(rr)})
+    np.testing.assert_allclose(host(got), want, rtol=1e-13)
+    no_r = c.jacobian({k: dev(v) for k, v in ang.items()})
+    np.testing.assert_allclose(host(no_r), want / rr, rtol=1e-13)
+    f32 = c.jacobian({k: dev(v.astype(np.float32)) for k, v in ang.items()})
+    assert f32.dtype == torch.float32
+    # float32: every factor c^p carries ~p ulp; deep random trees have p up to 32 and may underflow
+    np.testing.assert_allclose(host(f32), want / rr, rtol=5e-4, atol=1e-30)
+
+
+def test_jacobian_standard_tree_and_broadcast():
+    c = us.create_standard(3)  # J = sin^2(theta0) * sin(theta1)
+    th = {k: torch.rand(1000, device=DEV, dtype=torch.float64) * 3 for k in c.s_nodes}
+    want = torch.sin(th["theta0"]) ** 2 * torch.sin(th["theta1"])
+    assert torch.allclose(c.jacobian(th), want, rtol=1e-13, atol=0)
+    # on the quadrature grid (broadcast 1-D axes): integrating J over the angle box gives the area
+    n = 40
+    ax = {"theta0": torch.linspace(0, torch.pi, n + 1, device=DEV, dtype=torch.float64)[:, None, None],
+          "theta1": torch.linspace(0, torch.pi, n + 1, device=DEV, dtype=torch.float64)[None, :, None],
+          "theta2": torch.linspace(0, 2 * torch.pi, 2 * n + 1, device=DEV, dtype=torch.float64)[None, None, :]}
+    J = c.jacobian(ax)
+    assert J.shape == (n + 1, n + 1, 2 * n + 1)
+    area = torch.trapezoid(torch.trapezoid(torch.trapezoid(J, ax["theta2"].ravel(), dim=2), ax["theta1"].ravel(), dim=1), ax["theta0"].ravel(), dim=0)
+    assert abs(area.item() - c.surface_area()) < 2e-2

@@ -259,17 +259,10 @@ class SphericalCoordinates[TSpherical, TCartesian]:
         """``r * prod cos^(S_cos+1) sin^(S_sin+1)`` with exponent 0 for leaf children.
 
         The reference's version (_coordinates.py:668-702) returns NaN for every tree because the
-        leaf entries of ``S`` are NaN; this is the intended formula.  Plain torch ops — it is not
-        on the hot path (``integrate`` folds the Jacobian into the Gauss–Jacobi weights).
+        leaf entries of ``S`` are NaN; this is the formula it intends (a deliberate fix), with the
+        reference's own convention of ``r`` to the first power.  One fused kernel launch
+        (``us_jacobian``); see ``_transform.jacobian``.
         """
-        import torch
+        from ._transform import jacobian
 
-        out: Any = spherical["r"] if "r" in spherical else 1
-        for node in self.s_nodes:
-            theta = spherical[node]
-            for kind, fn in (("cos", torch.cos), ("sin", torch.sin)):
-                child = get_child(self.G, node, kind)
-                power = 0 if self.G.out_degree(child) == 0 else int(self.S[child]) + 1
-                if power:
-                    out = out * fn(theta) ** power
-        return out
+        return jacobian(self, spherical)

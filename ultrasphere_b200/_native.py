@@ -61,6 +61,11 @@ _SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
         C.c_int,
         [C.POINTER(UsPlan), C.c_int, C.c_int64, C.c_int, _PI64, _PP, _PU32, C.c_void_p, C.c_uint32, _PP, C.c_void_p, C.c_int64, C.c_void_p],
     ),
+    "us_jacobian": (
+        C.c_int,
+        [C.POINTER(UsPlan), C.c_int, C.c_int64, C.c_int, _PI64, _PP, _PU32, C.c_void_p, C.c_uint32,
+         C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p, C.c_void_p],
+    ),
     "us_from_cartesian": (
         C.c_int,
         [C.POINTER(UsPlan), C.c_int, C.c_int64, C.c_int, _PI64, _PP, _PU32, C.c_void_p, _PP, C.c_void_p],

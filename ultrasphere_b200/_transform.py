@@ -500,3 +500,54 @@ def _launch_from(
         )
     _native.check(status, "us_from_cartesian")
     return out
+
+
+# --------------------------------------------------------------------------------------
+# jacobian
+# --------------------------------------------------------------------------------------
+def jacobian(c: SphericalCoordinates[Any, Any], spherical: Mapping[Any, Any]) -> Any:
+    """``r * prod cos(theta)^(S_cos+1) * sin(theta)^(S_sin+1)`` (exponent 0 for leaf children) in one
+    fused launch (``us_jacobian``).  Shapes broadcast like ``to_cartesian(as_array=True)``."""
+    from ._coordinates import get_child
+
+    angles_in = [spherical[k] for k in c.s_nodes]
+    r_in = spherical["r"] if "r" in spherical else 1
+    if c.s_ndim == 0:
+        return r_in
+    r_is_tensor = isinstance(r_in, torch.Tensor)
+    tensors = angles_in + ([r_in] if r_is_tensor else [])
+    device = _require_cuda_tensors(tensors, "jacobian")
+    dtype = _compute_dtype(tensors)
+    if not r_is_tensor:
+        r_in = None if r_in == 1 else torch.full((), float(r_in), dtype=dtype, device=device)
+    angles = [a if a.dtype == dtype else a.to(dtype) for a in angles_in]
+    r = None if r_in is None else (r_in if r_in.dtype == dtype else r_in.to(dtype))
+    ct = plan_for(c)
+    cos_pow, sin_pow = [], []
+    for node in c.s_nodes:
+        for kind, out in (("cos", cos_pow), ("sin", sin_pow)):
+            child = get_child(c.G, node, kind)
+            out.append(0 if c.G.out_degree(child) == 0 else int(c.S[child]) + 1)
+    full = tuple(torch.broadcast_shapes(*[t.shape for t in angles + ([r] if r is not None else [])]))
+    geo = _Geometry(list(angles) + [r], full)
+    out = torch.empty(full, dtype=dtype, device=device)
+    if geo.n == 0:
+        return out
+    with device_guard(device):
+        status = _native.lib().us_jacobian(
+            C.byref(ct.plan),
+            _DTYPE_CODE[dtype],
+            geo.n,
+            len(geo.shape),
+            _native.i64_array(geo.shape),
+            _native.void_p_array([t.data_ptr() for t in geo.tensors[:-1]]),
+            _native.u32_array(geo.masks[:-1]),
+            _ptr(geo.tensors[-1]),
+            geo.masks[-1],
+            (C.c_int32 * ct.n_nodes)(*cos_pow),
+            (C.c_int32 * ct.n_nodes)(*sin_pow),
+            out.data_ptr(),
+            _stream_ptr(device),
+        )
+    _native.check(status, "us_jacobian")
+    return out

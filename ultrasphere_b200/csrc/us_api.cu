@@ -160,6 +160,27 @@ extern "C" int64_t us_to_cartesian_workspace_bytes(const us_plan_t* plan, int dt
   return bcast_workspace_bytes(plan, dtype, n, ndim, shape, angle_mask);
 }
 
+extern "C" int us_jacobian(const us_plan_t* plan, int dtype, int64_t n, int ndim, const int64_t* shape,
+                           const void* const* angle_dev, const uint32_t* angle_mask, const void* r_dev,
+                           uint32_t r_mask, const int32_t* cos_pow, const int32_t* sin_pow, void* out_dev,
+                           void* stream) {
+  static const char* who = "us_jacobian";
+  XformParams p;
+  memset(&p, 0, sizeof p);
+  if (int rc = fill_common(p, plan, dtype, n, ndim, shape, who)) return rc;
+  if (!angle_dev || !angle_mask || !cos_pow || !sin_pow || (!out_dev && n > 0)) return fail(US_EINVAL, "%s: null pointer", who);
+  for (int s = 0; s < plan->n_nodes; ++s) {
+    if (!angle_dev[s] && n > 0) return fail(US_EINVAL, "%s: angle %d is null", who, s);
+    p.in[s] = angle_dev[s];
+    p.in_mask[s] = angle_mask[s];
+  }
+  p.out[0] = out_dev;
+  p.r_in = r_dev;
+  p.r_mask = r_mask;
+  if (n == 0) return 0;
+  return launch_jacobian_strided(p, cos_pow, sin_pow, dtype, (cudaStream_t)stream);
+}
+
 extern "C" int us_from_cartesian(const us_plan_t* plan, int dtype, int64_t n, int ndim, const int64_t* shape,
                                  const void* const* x_dev, const uint32_t* x_mask, void* r_out_dev,
                                  void* const* angle_out_dev, void* stream) {

@@ -24,6 +24,7 @@ static_assert(sizeof(XformParams) < 32000, "kernel parameter block must fit the 
 
 int launch_to_cartesian_strided(const XformParams& p, int dtype, cudaStream_t st);
 int launch_from_cartesian_strided(const XformParams& p, int dtype, cudaStream_t st);
+int launch_jacobian_strided(const XformParams& p, const int32_t* cos_pow, const int32_t* sin_pow, int dtype, cudaStream_t st);
 
 // broadcast path of to_cartesian (us_transform_bcast.cu): sincos tables for broadcast angles
 int64_t bcast_workspace_bytes(const us_plan_t* plan, int dtype, int64_t n, int ndim, const int64_t* shape, const uint32_t* angle_mask);

@@ -7,6 +7,8 @@
 // is what integrands inside integrate() pass: s_ndim one-dimensional axes of a tensor grid.
 //
 // Reference semantics: src/ultrasphere/_coordinates.py:555-579 (from) and :636-656 (to).
+#include <mutex>
+
 #include "us_common.cuh"
 #include "us_params.cuh"
 
@@ -149,6 +151,65 @@ __global__ void __launch_bounds__(256) from_cartesian_strided(const __grid_const
     if (o) st_stream(o + i, av[0]);
     cur = nv[0];
   }
+}
+
+// x^e for a small non-negative integer e (exponentiation by squaring, warp-uniform control flow)
+template <typename T>
+__device__ __forceinline__ T powi(T x, int e) {
+  T acc = T(1);
+  while (e > 0) {
+    if (e & 1) acc *= x;
+    x *= x;
+    e >>= 1;
+  }
+  return acc;
+}
+
+// jacobian: out = r * prod_k cos(theta_k)^a_k * sin(theta_k)^b_k; exponents ride in the low / high
+// 16 bits of in_mask's neighbour table `pow` (one word per node)
+struct JacobianParams {
+  XformParams x;
+  uint32_t pow[US_MAX_NODES];  // cos exponent | sin exponent << 16, s_nodes order
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) jacobian_strided(const __grid_constant__ JacobianParams jp) {
+  const XformParams& p = jp.x;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n) return;
+  Indexer ix(p, i);
+  T acc = p.r_in ? ld_stream((const T*)p.r_in + ix.off(p.r_mask)) : T(1);
+  const int nn = p.plan.n_nodes;
+  for (int s = 0; s < nn; ++s) {
+    const uint32_t e = jp.pow[s];
+    if (e == 0) continue;  // both children are leaves: the node contributes nothing
+    const T thv[1] = {ld_stream((const T*)p.in[s] + ix.off(p.in_mask[s]))};
+    T sv[1], cv[1];
+    sincos_vec<1>(thv, sv, cv);
+    acc *= powi(cv[0], (int)(e & 0xFFFFu)) * powi(sv[0], (int)(e >> 16));
+  }
+  st_stream((T*)p.out[0] + i, acc);
+}
+
+int launch_jacobian_strided(const XformParams& p, const int32_t* cos_pow, const int32_t* sin_pow, int dtype, cudaStream_t st) {
+  static JacobianParams jp;  // 10.5 KB parameter block; copied at launch, guarded for concurrent callers
+  static std::mutex lock;
+  std::lock_guard<std::mutex> guard(lock);
+  jp.x = p;
+  for (int s = 0; s < p.plan.n_nodes; ++s) {
+    if (cos_pow[s] < 0 || cos_pow[s] > 0xFFFF || sin_pow[s] < 0 || sin_pow[s] > 0xFFFF)
+      return fail(US_EINVAL, "us_jacobian: exponent of node %d out of range", s);
+    jp.pow[s] = (uint32_t)cos_pow[s] | ((uint32_t)sin_pow[s] << 16);
+  }
+  const int threads = 256;
+  const int64_t blocks = (p.n + threads - 1) / threads;
+  if (blocks > 0x7FFFFFFFLL) return fail(US_EINVAL, "us_jacobian: n too large for one launch");
+  if (dtype == US_F32)
+    jacobian_strided<float><<<(unsigned)blocks, threads, 0, st>>>(jp);
+  else
+    jacobian_strided<double><<<(unsigned)blocks, threads, 0, st>>>(jp);
+  US_CUDA_TRY(cudaGetLastError(), "jacobian_strided launch");
+  return 0;
 }
 
 int launch_to_cartesian_strided(const XformParams& p, int dtype, cudaStream_t st) {
