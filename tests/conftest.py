@@ -10,6 +10,12 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # the shared library is a build artefact (git-ignored): build it once if a fresh checkout lacks it
+    lib = os.path.join(ROOT, "ultrasphere_b200", "lib", "libultrasphere_b200.so")
+    if not os.path.isfile(lib):
+        import subprocess
+
+        subprocess.run(["make", "-C", os.path.join(ROOT, "ultrasphere_b200", "csrc")], check=True)
 
 
 def pytest_collection_modifyitems(config, items):
