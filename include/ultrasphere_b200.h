@@ -50,7 +50,8 @@ extern "C" {
 #define US_MAX_LEAVES (US_MAX_NODES + 1)
 #define US_MAX_DIMS 12   /* broadcast dims of the strided path after collapsing */
 #define US_MAX_STACK 64  /* pending `c` branches of the pre-order program */
-#define US_MAX_AXES 64   /* axes per us_separable_reduce call */
+#define US_MAX_AXES 64   /* axes per us_separable_reduce / us_quadrature_rules call */
+#define US_MAX_RULE_POINTS 2048 /* Gauss points per axis of us_quadrature_rules (48 KB of coefficients) */
 
 /* element types (the path computes in the type it is given) */
 #define US_F32 0
@@ -203,6 +204,28 @@ US_API int us_random_ball(int dtype, int dim, int64_t n, uint64_t seed, int surf
  */
 US_API int us_random_uniform(int dtype, int count, int64_t n, uint64_t seed, const double* lo,
                              const double* hi, void* const* out_dev, void* stream);
+
+/*
+ * ---- "next" row: the 1-D rules of roots() built on the device ----
+ * One launch fills the angle and weight tables of n_axes angles (reference: the per-node loop of
+ * roots(), src/ultrasphere/_integral.py:83-109, whose Gauss rules come from the host call
+ * scipy.special.roots_jacobi followed by one H2D copy per table).  Per axis i:
+ *   kind US_NODE_A : count[i] = 2n points  x_j = j*pi/n, w_j = pi/n   (_integral.py:85-87), rounded
+ *                    in the output type exactly as torch's CUDA kernels round `arange(2n)*pi/n`
+ *   kind US_NODE_B : count[i] Gauss-Jacobi(alpha, beta) points t_j, x_j = acos(t_j)     (:88-92)
+ *   kind US_NODE_BP: x_j = asin(t_j)                                                    (:93-97)
+ *   kind US_NODE_C : x_j = acos(t_j)/2, w_j divided by 2^(alpha+beta+2)                 (:98-105)
+ * (alpha, beta) are passed exactly as the reference passes them to roots_jacobi.  The Gauss nodes
+ * are the eigenvalues of the same Jacobi matrix scipy diagonalises, found per root by Sturm
+ * multisection + Newton; weights are Christoffel sums.  Agreement with roots_jacobi: nodes
+ * <= 2.3e-16 absolute, weights within scipy's own error (both checked against 50-digit arithmetic
+ * in tests/test_gpu_rules.py).  Tables ascend in t like scipy's.
+ * dtype[i] is US_F32 / US_F64 per axis (the reference's dtype=None gives float32 trapezoid tables
+ * next to float64 Gauss tables); x_dev[i], w_dev[i]: count[i] elements each.
+ */
+US_API int us_quadrature_rules(int n_axes, const uint8_t* kind, const int64_t* count, const double* alpha,
+                               const double* beta, const int32_t* dtype, void* const* x_dev,
+                               void* const* w_dev, void* stream);
 
 /*
  * Measurement helper: runs a dependent-free DFMA (dtype=US_F64) or FFMA (US_F32) loop on every

@@ -147,6 +147,31 @@ def test_argument_errors_do_not_need_a_gpu():
     assert b"null plan" in lib.us_last_error_string()
     assert lib.us_weighted_reduce(7, 1, None, None, None, 1, None, 0, None, 0, None) == -1
     assert lib.us_separable_reduce(0, 0, None, None, None, None, None, None) == -2
+    assert lib.us_quadrature_rules(_native.US_MAX_AXES + 1, None, None, None, None, None, None, None, None) == -2
+    assert lib.us_quadrature_rules(1, None, None, None, None, None, None, None, None) == -1
+    assert lib.us_quadrature_rules(0, None, None, None, None, None, None, None, None) == 0
+
+
+def test_rule_backend_switch_and_rule_parameters():
+    from ultrasphere_b200._integral import _rule_parameters
+
+    assert us.set_rule_backend("scipy") == "scipy"
+    with pytest.raises(ValueError):
+        us.set_rule_backend("numpy")
+    with us.rule_backend("device"):
+        assert us.set_rule_backend("device") == "device"
+        with pytest.raises(RuntimeError, match="CUDA devices only"):
+            us.roots(us.create_spherical(), 4, expand_dims_x=False, xp=torch, device="cpu")
+        with pytest.raises(ValueError, match="positive integer"):
+            us.roots(us.create_spherical(), 0, expand_dims_x=False, xp=torch, device="cuda")
+    assert us.set_rule_backend("scipy") == "scipy"
+    # (alpha, beta) are what the reference hands to roots_jacobi (_integral.py:88-103)
+    c = us.create_from_branching_types("cbaa")  # theta0: c (cos->theta1: b, sin->theta2: a)
+    got = {str(node): _rule_parameters(c, node) for node in c.s_nodes}
+    S = {str(k): v for k, v in c.S.items()}
+    assert got["theta0"][0] == "c" and got["theta0"][1:] == (S["theta1"] / 2, S["theta2"] / 2)
+    kinds = sorted(v[0] for v in got.values())
+    assert kinds == ["a", "a", "b", "c"] or kinds == ["a", "b", "c"]
 
 
 def test_no_cpu_fallback():

@@ -22,6 +22,19 @@ def t(fn, reps=5):
         e0.record(); fn(); e1.record(); e1.synchronize(); best = min(best, e0.elapsed_time(e1))
     return best
 
+def t_graph(fn, calls=20, reps=5):
+    """Per-call device time with the host launch cost removed: `calls` launches captured in one CUDA graph."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn()
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(calls):
+            keep = fn()
+    return t(g.replay, reps) / calls
+
 out = {}
 for spec, dt, n in CONFIGS:
     if only and only not in spec:
@@ -35,6 +48,10 @@ for spec, dt, n in CONFIGS:
         "from_ms": tf, "to_ms": tt, "from_gpts": n / tf / 1e6, "to_gpts": n / tt / 1e6,
         "from_frac_hbm": n * bpp / tf / 1e6 / peak, "to_frac_hbm": n * bpp / tt / 1e6 / peak, "bytes_per_point": bpp,
     }
+    if n <= 4_000_000:  # launch-bound sizes: the same calls replayed from a CUDA graph
+        gf = t_graph(lambda: c.from_cartesian(x)); gt = t_graph(lambda: c.to_cartesian(s, as_array=True))
+        out[f"{spec}|{str(dt)[6:]}|{n}"].update({"graph_from_ms": gf, "graph_to_ms": gt,
+            "graph_from_frac_hbm": n * bpp / gf / 1e6 / peak, "graph_to_frac_hbm": n * bpp / gt / 1e6 / peak})
     del x, s
     torch.cuda.empty_cache()
 print(json.dumps(out, indent=1))

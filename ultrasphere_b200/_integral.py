@@ -6,7 +6,10 @@ and :157-276 (``integrate``) with ``xp=torch`` on a CUDA device.
 * The 1-D rules come from the very same host call the reference makes
   (``scipy.special.roots_jacobi``; trapezoid for type ``a``) so nodes and weights are bit-identical;
   the reference's argument order for type ``c`` — ``(S_cos/2, S_sin/2)`` as ``(alpha, beta)`` — is
-  reproduced on purpose.
+  reproduced on purpose.  ``rule_backend("device")`` builds all tables of a
+  coordinate system in one kernel launch instead (``us_quadrature_rules``: no scipy call, no H2D
+  copy; nodes within 1 ulp of scipy's, weights more accurate than scipy's) — for workloads of
+  many small integrals whose ``n`` changes from call to call.
 * The contraction ``sum_grid prod_i w_i * f`` is ONE fused pass over the integrand's values
   (``us_weighted_reduce``: warp-shuffle + block tree, float64 accumulation, fixed cross-block
   order) instead of ``s_ndim`` successive ``vecdot`` passes; the separable branch is one launch of
@@ -17,8 +20,10 @@ and :157-276 (``integrate``) with ``xp=torch`` on a CUDA device.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import functools
+import os
 from collections.abc import Callable, Mapping
 from typing import Any
 
@@ -35,6 +40,33 @@ from ._transform import _DTYPE_CODE, _stream_ptr, device_guard
 # grid most integrands build comes on top).  Measured on B200 (tools/c5_breakdown.py): smaller,
 # L2-sized slabs are slower than one pass because of the extra launches, so the default is large.
 DEFAULT_SLAB_BYTES = 2 << 30
+
+
+_RULE_BACKENDS = ("scipy", "device")
+_rule_backend = os.environ.get("ULTRASPHERE_B200_RULES", "scipy")
+if _rule_backend not in _RULE_BACKENDS:
+    raise ValueError(f"ULTRASPHERE_B200_RULES={_rule_backend!r}: expected one of {_RULE_BACKENDS}")
+
+
+def set_rule_backend(name: str) -> str:
+    """Choose where ``roots`` builds the Gauss–Jacobi tables: ``"scipy"`` (host, bit-identical to
+    the reference's, cached per ``(n, alpha, beta)``) or ``"device"`` (one kernel launch per
+    coordinate system).  Returns the previous setting."""
+    global _rule_backend
+    if name not in _RULE_BACKENDS:
+        raise ValueError(f"rule backend {name!r}: expected one of {_RULE_BACKENDS}")
+    previous, _rule_backend = _rule_backend, name
+    return previous
+
+
+@contextlib.contextmanager
+def rule_backend(name: str) -> Any:
+    """``with rule_backend("device"): ...`` — scoped :func:`set_rule_backend`."""
+    previous = set_rule_backend(name)
+    try:
+        yield
+    finally:
+        set_rule_backend(previous)
 
 
 def _check_xp(xp: Any) -> None:
@@ -64,23 +96,94 @@ def _jacobi_rule(kind: str, n: int, alpha: float, beta: float) -> tuple[np.ndarr
     return x, w
 
 
-def _host_rule(c: SphericalCoordinates[Any, Any], node: Any, n: int) -> tuple[np.ndarray, np.ndarray] | None:
-    """float64 nodes/weights of one angle on the host; None for type `a` (built on the device)."""
+def _rule_parameters(c: SphericalCoordinates[Any, Any], node: Any) -> tuple[str, float, float]:
+    """``(kind, alpha, beta)`` of one angle's rule, the Jacobi parameters being what the reference
+    hands to ``roots_jacobi`` (_integral.py:88-103)."""
     kind = c.branching_types[node]
     if kind == BranchingType.A:
-        return None
+        return "a", 0.0, 0.0
     if kind == BranchingType.B:
         beta = c.S[get_child(c.G, node, "sin")] / 2
-        return _jacobi_rule("b", n, beta, beta)
+        return "b", beta, beta
     if kind == BranchingType.BP:
         alpha = c.S[get_child(c.G, node, "cos")] / 2
-        return _jacobi_rule("b'", n, alpha, alpha)
+        return "b'", alpha, alpha
     if kind == BranchingType.C:
         # the reference passes (S_cos/2, S_sin/2) as (alpha, beta): reproduced (SURVEY.md App. A.1)
-        alpha = c.S[get_child(c.G, node, "cos")] / 2
-        beta = c.S[get_child(c.G, node, "sin")] / 2
-        return _jacobi_rule("c", n, alpha, beta)
+        return "c", c.S[get_child(c.G, node, "cos")] / 2, c.S[get_child(c.G, node, "sin")] / 2
     raise ValueError(f"Invalid branching type {kind}.")
+
+
+def _host_rule(c: SphericalCoordinates[Any, Any], node: Any, n: int) -> tuple[np.ndarray, np.ndarray] | None:
+    """float64 nodes/weights of one angle on the host; None for type `a` (built on the device)."""
+    kind, alpha, beta = _rule_parameters(c, node)
+    if kind == "a":
+        return None
+    return _jacobi_rule(kind, n, alpha, beta)
+
+
+_KIND_CODE = {"a": 0, "b": 1, "b'": 2, "c": 3}  # US_NODE_* of include/ultrasphere_b200.h
+
+
+def _rules_on_device(
+    c: SphericalCoordinates[Any, Any], n: int, device: Any | None, dtype: Any | None
+) -> list[tuple[torch.Tensor, torch.Tensor]]:
+    """All 1-D tables of ``c`` from one launch of ``us_quadrature_rules`` (s_nodes order)."""
+    if int(n) != n or n < 1:
+        raise ValueError("n must be a positive integer.")
+    n = int(n)
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError(f"device={device}: the device rule backend builds its tables on CUDA devices only")
+    native = dtype in (None, torch.float32, torch.float64)
+    default = torch.get_default_dtype() if torch.get_default_dtype() in _DTYPE_CODE else torch.float32
+    kinds, counts, alphas, betas, dtypes = [], [], [], [], []
+    for node in c.s_nodes:
+        kind, alpha, beta = _rule_parameters(c, node)
+        # dtype=None in the reference: `arange(2n) * pi / n` is torch's default float type, the
+        # scipy tables stay float64 (SURVEY.md App. A.2)
+        t = (dtype if dtype is not None else (default if kind == "a" else torch.float64)) if native else torch.float64
+        count = 2 * n if kind == "a" else n
+        if kind != "a" and count > _native.US_MAX_RULE_POINTS:
+            raise ValueError(
+                f"n={n}: the device rule backend holds at most {_native.US_MAX_RULE_POINTS} Gauss points per angle "
+                '(use set_rule_backend("scipy"))'
+            )
+        kinds.append(_KIND_CODE[kind])
+        counts.append(count)
+        alphas.append(float(alpha))
+        betas.append(float(beta))
+        dtypes.append(t)
+    # one allocation per dtype; the tables are 16-byte aligned views into it (x then w of each angle)
+    steps = [(k + 3) & ~3 for k in counts]
+    pools = {t: torch.empty(2 * sum(k for k, u in zip(steps, dtypes) if u == t), dtype=t, device=device) for t in set(dtypes)}
+    used = dict.fromkeys(pools, 0)
+    tables = []
+    for count, step, t in zip(counts, steps, dtypes):
+        at = used[t]
+        tables.append((pools[t][at : at + count], pools[t][at + step : at + step + count]))
+        used[t] = at + 2 * step
+    dtypes = [_DTYPE_CODE[t] for t in dtypes]
+    lib = _native.lib()
+    for lo in range(0, len(kinds), _native.US_MAX_AXES):
+        hi = min(len(kinds), lo + _native.US_MAX_AXES)
+        k = hi - lo
+        with device_guard(device):
+            status = lib.us_quadrature_rules(
+                k,
+                (C.c_uint8 * k)(*kinds[lo:hi]),
+                _native.i64_array(counts[lo:hi]),
+                (C.c_double * k)(*alphas[lo:hi]),
+                (C.c_double * k)(*betas[lo:hi]),
+                (C.c_int32 * k)(*dtypes[lo:hi]),
+                _native.void_p_array([x.data_ptr() for x, _ in tables[lo:hi]]),
+                _native.void_p_array([w.data_ptr() for _, w in tables[lo:hi]]),
+                _stream_ptr(device),
+            )
+        _native.check(status, "us_quadrature_rules")
+    if not native:
+        tables = [(x.to(dtype), w.to(dtype)) for x, w in tables]
+    return tables
 
 
 def roots(
@@ -97,9 +200,11 @@ def roots(
     _check_xp(xp)
     xs: dict[Any, torch.Tensor] = {}
     ws: dict[Any, torch.Tensor] = {}
+    on_device = _rules_on_device(c, n, device, dtype) if _rule_backend == "device" else None
     for i, node in enumerate(c.s_nodes):
-        rule = _host_rule(c, node, n)
-        if rule is None:
+        if on_device is not None:
+            x, w = on_device[i]
+        elif (rule := _host_rule(c, node, n)) is None:
             x = torch.arange(2 * n, device=device, dtype=dtype) * torch.pi / n
             w = torch.ones(2 * n, device=device, dtype=dtype) * torch.pi / n
         else:
@@ -268,7 +373,7 @@ def _device_rules(
     H2D copies of the tables are synchronous pageable copies, ~20 us each).  The integrand receives
     copies of the angle tensors, so an in-place edit cannot poison the cache."""
     cache = c.__dict__.setdefault("_quad_cache", {})
-    key = (n, dtype, device, expand)
+    key = (n, dtype, device, expand, _rule_backend)
     hit = cache.get(key)
     if hit is None:
         if len(cache) >= 16:

@@ -15,6 +15,7 @@ US_MAX_LEAVES = US_MAX_NODES + 1
 US_MAX_DIMS = 12
 US_MAX_STACK = 64
 US_MAX_AXES = 64
+US_MAX_RULE_POINTS = 2048
 US_F32, US_F64 = 0, 1
 US_ABI_VERSION = 1
 
@@ -80,6 +81,10 @@ _SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     "us_random_uniform": (
         C.c_int,
         [C.c_int, C.c_int, C.c_int64, C.c_uint64, C.POINTER(C.c_double), C.POINTER(C.c_double), _PP, C.c_void_p],
+    ),
+    "us_quadrature_rules": (
+        C.c_int,
+        [C.c_int, C.POINTER(C.c_uint8), _PI64, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32), _PP, _PP, C.c_void_p],
     ),
     "us_probe_fma_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "us_math_probe_f32": (C.c_int, [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
