@@ -7,7 +7,8 @@ import ultrasphere_b200 as us
 from tests.helpers import make
 
 dev = torch.device("cuda:0")
-CONFIGS = [("spherical", torch.float64, 1_000_000), ("spherical", torch.float64, 64_000_000), ("hopf:3", torch.float64, 128_000_000),
+CONFIGS = [("spherical", torch.float64, 100_000), ("spherical", torch.float64, 300_000), ("spherical", torch.float64, 1_000_000), ("spherical", torch.float64, 4_000_000),
+           ("standard:9", torch.float32, 1_000_000), ("standard:9", torch.float32, 4_000_000), ("spherical", torch.float64, 64_000_000), ("hopf:3", torch.float64, 128_000_000),
            ("standard_prime:8", torch.float64, 128_000_000), ("random:32:0", torch.float32, 64_000_000), ("standard:9", torch.float64, 128_000_000)]
 only = os.environ.get("US_ONLY")
 peak = 6536.4

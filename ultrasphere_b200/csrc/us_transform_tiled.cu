@@ -385,7 +385,16 @@ static int try_tiled(const XformParams& p, int dtype, cudaStream_t st) {
     if (rc != 0) return rc;
     n_tiles = p.n / P;
   } else {
-  if (n_tiles < 2 * sm_count()) return kNotTaken;  // small batches: the strided kernel is launch-bound anyway
+  {
+    static int64_t min_tiles = -1;  // US_TILED_MIN_TILES=<n>: tuning override of the small-batch cut-over
+    if (min_tiles < 0) {
+      const char* e = getenv("US_TILED_MIN_TILES");
+      min_tiles = e ? atoll(e) : 4 * sm_count();
+    }
+    // small batches: below ~4 tiles per SM the pipeline's fill/drain costs more than it hides
+    // (measured under CUDA-graph replay, create_spherical float64: 3e5 points 7.2 us strided vs 9.9 us tiled)
+    if (n_tiles < min_tiles) return kNotTaken;
+  }
   const void* fn = pick<TO>(dtype, v, p.plan.max_stack > 0, chain_kind(p.plan));
   const size_t smem = (size_t)kStages * n_rows * P * esz + sizeof(TileShared);
   int per_sm = 0;
