@@ -324,6 +324,55 @@ def test_stream_and_device_handling():
     assert torch.allclose(back, x, atol=1e-14)
 
 
+def test_concurrent_host_threads_and_streams():
+    """The library keeps no per-call global state (parameter blocks travel by value, the few
+    static blocks are mutex-guarded): host threads on their own streams, different trees, grids
+    and integrals running at once give the bits of a serial run."""
+    import threading
+
+    specs = ["standard:9", "hopf:3", "random:32:0", "cbaa", "standard:4", "spherical"]
+    trees = [make(us, s) if ":" in s or s == "spherical" else us.create_from_branching_types(s) for s in specs]
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    xs = [torch.rand((c.c_ndim, 200_003 + 1024 * i), device=DEV, dtype=torch.float64 if i % 2 else torch.float32, generator=gen) * 2 - 1 for i, c in enumerate(trees)]
+
+    def work(c, x):
+        s = c.from_cartesian(x)
+        back = c.to_cartesian(s, as_array=True)
+        jac = c.jacobian(s)
+        if c.s_ndim > 9:  # a tensor grid over 32 angles does not exist
+            return [*s.values(), back, jac]
+        ang, wts = us.roots(c, 5, expand_dims_x=True, xp=torch, device=DEV, dtype=torch.float64)
+        grid = c.to_cartesian(ang, as_array=True)
+        area = us.integrate(c, lambda a: 1 + 0 * c.to_cartesian(a, as_array=True)[0], False, 5, xp=torch, device=DEV, dtype=torch.float64)
+        return [*s.values(), back, jac, grid, area]
+
+    serial = [work(c, x) for c, x in zip(trees, xs)]
+    torch.cuda.synchronize()
+    results, errors = [None] * len(trees), []
+
+    def run(i):
+        try:
+            st = torch.cuda.Stream()
+            st.wait_stream(torch.cuda.default_stream())
+            with torch.cuda.stream(st):
+                for _ in range(6):
+                    out = work(trees[i], xs[i])
+            st.synchronize()
+            results[i] = out
+        except Exception as e:  # noqa: BLE001
+            errors.append((i, repr(e)))
+
+    threads = [threading.Thread(target=run, args=(i,)) for i in range(len(trees))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for i, (a, b) in enumerate(zip(serial, results)):
+        for u, v in zip(a, b):
+            assert torch.equal(u.nan_to_num(), v.nan_to_num()), specs[i]
+
+
 @pytest.mark.parametrize("spec,ndt,n", [("standard:9", np.float32, 1 << 22), ("hopf:3", np.float64, 1 << 21), ("random:32:0", np.float32, 1 << 20)])
 def test_million_point_parity(spec, ndt, n):
     """The first 2^20+ points of the benchmark configs against the oracle."""
