@@ -324,6 +324,46 @@ def test_stream_and_device_handling():
     assert torch.allclose(back, x, atol=1e-14)
 
 
+def test_more_than_2_pow_31_points():
+    """Element offsets past 2^31 (a 17 GB array per leaf set): 64-bit indexing in the tile kernels,
+    the ragged tail and the strided kernels.  Checked against the oracle on windows around the
+    start, the 2^31 boundary and the end, and by the round trip over the whole batch."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 80 << 30:
+        pytest.skip("needs 80 GB of free device memory")
+    c, t = us.create_polar(), vo.make("polar")
+    n = (1 << 31) + 4100  # rows stay 16-byte aligned (tile kernels) and leave a ragged tail of 4 points
+    x = torch.empty((2, n), device=DEV, dtype=torch.float32)
+    gen = torch.Generator(device=DEV).manual_seed(77)
+    for lo in range(0, n, 1 << 28):  # fill in pieces: rand() of 2^32 elements at once is not needed
+        hi = min(n, lo + (1 << 28))
+        x[:, lo:hi] = torch.rand((2, hi - lo), device=DEV, dtype=torch.float32, generator=gen) * 2 - 1
+    s = c.from_cartesian(x)
+    assert s["r"].shape == (n,)
+    windows = [(0, 5000), ((1 << 31) - 3000, (1 << 31) + 3000), (n - 5000, n)]
+    for lo, hi in windows:
+        want = vo.from_cartesian(t, host(x[:, lo:hi]))
+        assert np.array_equal(host(s["r"][lo:hi]), want["r"]), (lo, hi)
+        for k in c.s_nodes:
+            assert_angles_close(host(s[k][lo:hi]), want[k], f"window {lo}")
+    back = c.to_cartesian(s, as_array=True)
+    worst = 0.0
+    for lo in range(0, n, 1 << 28):
+        hi = min(n, lo + (1 << 28))
+        worst = max(worst, (back[:, lo:hi] - x[:, lo:hi]).abs().max().item())
+    assert worst <= 1e-6, worst  # a few float32 ulp of |x| <= 1.41 over 2.1e9 points
+    # the strided kernels on the same size: a stride-2 view of a wider buffer is not tile-eligible
+    del back, s
+    torch.cuda.empty_cache()
+    y = x[:, 1:]  # misaligned rows (offset by one element): strided path over 2^31 + 4099 points
+    s2 = c.from_cartesian(y)
+    for lo, hi in [((1 << 31) - 2000, (1 << 31) + 2000), (n - 3001, n - 1)]:
+        want = vo.from_cartesian(t, host(y[:, lo:hi]))
+        assert np.array_equal(host(s2["r"][lo:hi]), want["r"]), (lo, hi)
+        for k in c.s_nodes:
+            assert_angles_close(host(s2[k][lo:hi]), want[k], f"strided window {lo}")
+
+
 def test_concurrent_host_threads_and_streams():
     """The library keeps no per-call global state (parameter blocks travel by value, the few
     static blocks are mutex-guarded): host threads on their own streams, different trees, grids
