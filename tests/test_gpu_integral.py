@@ -197,6 +197,32 @@ def test_weighted_reduce_long_inner_axis_and_single_axis():
     assert abs(got - float(w1 @ v1)) <= 1e-12 * float(w1 @ np.abs(v1))
 
 
+def test_weighted_reduce_past_2_pow_31_values():
+    """A 2.1e9-value integrand (8.6 GB of float32): 64-bit offsets in the TMA slab ring, the row
+    weights and the two-phase final sum.  Values depend on the row so a dropped or doubled slab
+    shows; the expected sum factorises."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 20 << 30:
+        pytest.skip("needs 20 GB of free device memory")
+    n0, n1, n2 = 2049, 1024, 1025  # 2049 * 1024 * 1025 = 2,150,630,400 > 2^31
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    row = torch.rand(n0, device=DEV, dtype=torch.float32, generator=gen) + 0.5
+    val = row[:, None, None].expand(n0, n1, n2).contiguous()
+    ws = [torch.rand(n, device=DEV, dtype=torch.float32, generator=gen) + 0.1 for n in (n0, n1, n2)]
+    got = us.weighted_reduce(val, ws).item()
+    want = ((ws[0].double() * row.double()).sum() * ws[1].double().sum() * ws[2].double().sum()).item()
+    assert abs(got - want) <= 1e-6 * want, (got, want)  # float32 products w0*w1*w2*val, float64 sums
+    # the same as a complex, trailing-axis integrand through the column kernel
+    del val
+    torch.cuda.empty_cache()
+    m = 40
+    v2 = (row[:, None, None] * torch.ones((1, 1024 * 13, m), device=DEV)).contiguous()  # 2049*13312*40 = 1.09e9
+    w2 = [ws[0], torch.rand(1024 * 13, device=DEV, generator=gen) + 0.1]
+    got2 = us.weighted_reduce(v2, w2)
+    want2 = ((w2[0].double() * row.double()).sum() * w2[1].double().sum()).item()
+    assert got2.shape == (m,) and (got2.double() - want2).abs().max().item() <= 1e-6 * want2
+
+
 def test_full_size_quadrature_matches_analytic():
     """BASELINE config 5: create_standard(4), n=96 (169,869,312 nodes), f = exp(k.x), float64."""
     k5 = np.random.default_rng(0).uniform(0, 1, 5)
