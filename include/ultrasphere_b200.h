@@ -175,6 +175,23 @@ US_API int us_separable_reduce(int dtype, int n_axes, const int64_t* len, const 
                         void* const* out_dev, void* stream);
 
 /*
+ * ---- the integrand's side of integrate(): a linear functional of the Cartesian coordinates ----
+ * out[j][g] = sum over leaves l of coef[j][l] * x_l[g],  x = to_cartesian(spherical)   (j < m)
+ * — what the reference's own quadrature test computes with
+ * `einsum("v,v...->...", k, c.to_cartesian(s, as_array=True))` (tests/test_integral.py:88-92) on the
+ * tensor grid of quadrature angles.  The leaf products are folded into the sum as they are formed
+ * (program order, one FMA per leaf) and never written: sizeof(T) instead of c_ndim*sizeof(T) bytes
+ * per grid point and no second pass.  Operands are addressed exactly as in us_to_cartesian_ws
+ * (launch shape + masks, optional sincos-table workspace of us_to_cartesian_workspace_bytes()).
+ * coef_dev : m * n_leaves device values of the compute dtype, row-major, c_nodes order
+ * out_dev  : m * n elements, row j at out + j*n
+ */
+US_API int us_to_cartesian_dot(const us_plan_t* plan, int dtype, int64_t n, int ndim, const int64_t* shape,
+                               const void* const* angle_dev, const uint32_t* angle_mask, const void* r_dev,
+                               uint32_t r_mask, const void* coef_dev, int m, void* out_dev,
+                               void* workspace_dev, int64_t workspace_bytes, void* stream);
+
+/*
  * ---- "next" row: SphericalCoordinates.jacobian (_coordinates.py:668-702) ----
  * out = r * prod over internal nodes of cos(theta)^cos_pow * sin(theta)^sin_pow, one fused pass that
  * shares the sincos with nothing else to write: (s_ndim + 2) * sizeof(T) bytes per point.  The

@@ -29,7 +29,11 @@ res["exp_ms"] = t(lambda: torch.exp(ph))
 wl = [ws[node] for node in c.s_nodes]
 res["weighted_reduce_ms"] = t(lambda: us.weighted_reduce(val, wl))
 res["weighted_reduce_gbs"] = nodes * 8 / res["weighted_reduce_ms"] / 1e6
+res["to_cartesian_dot_ms"] = t(lambda: c.to_cartesian_dot(xs, k))
+res["to_cartesian_dot_write_gbs"] = nodes * 8 / res["to_cartesian_dot_ms"] / 1e6
 del X, ph, val
+ffused = lambda s: torch.exp(c.to_cartesian_dot(s, k))
+res["integrate_fused_integrand_ms"] = t(lambda: us.integrate(c, ffused, False, n, xp=torch, device=dev, dtype=torch.float64))
 f = lambda s: torch.exp(torch.einsum("v,v...->...", k, c.to_cartesian(s, as_array=True)))
 for slab in (0, 16 << 20, 48 << 20, 256 << 20):
     res[f"integrate_slab_{slab>>20}MB_ms"] = t(lambda: us.integrate(c, f, False, n, xp=torch, device=dev, dtype=torch.float64, slab_bytes=slab))

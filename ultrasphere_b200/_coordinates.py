@@ -255,6 +255,17 @@ class SphericalCoordinates[TSpherical, TCartesian]:
 
         return to_cartesian(self, spherical, as_array=as_array)
 
+    def to_cartesian_dot(self, spherical: Mapping[Any, Any], k: Any, /) -> Any:
+        """``sum_v k[v] * x_v`` for ``x = to_cartesian(spherical, as_array=True)`` — the reference
+        spells it ``einsum("v,v...->...", k, c.to_cartesian(s, as_array=True))``
+        (tests/test_integral.py:88-92) — fused into the transform: the Cartesian grid is never
+        written, which matters inside ``integrate`` where it is ``c_ndim`` times the size of the
+        integrand.  ``k``: ``(c_ndim,)`` or ``(m, c_ndim)`` in ``c_nodes`` order.  An extension:
+        the reference has no such method."""
+        from ._transform import to_cartesian_dot
+
+        return to_cartesian_dot(self, spherical, k)
+
     def jacobian(self, spherical: Mapping[Any, Any], /) -> Any:
         """``r * prod cos^(S_cos+1) sin^(S_sin+1)`` with exponent 0 for leaf children.
 

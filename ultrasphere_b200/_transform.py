@@ -347,6 +347,74 @@ def _launch_to(
     return out
 
 
+def to_cartesian_dot(c: SphericalCoordinates[Any, Any], spherical: Mapping[Any, Any], k: Any) -> torch.Tensor:
+    """``einsum("v,v...->...", k, to_cartesian(spherical, as_array=True))`` without materialising the
+    Cartesian coordinates (``us_to_cartesian_dot``).  ``k``: ``(c_ndim,)`` or ``(m, c_ndim)``
+    coefficients in ``c_nodes`` order (tensor on any device, or numbers); returns the broadcast
+    shape of the inputs, with a leading ``m`` axis for a matrix ``k``."""
+    angles_in = [spherical[key] for key in c.s_nodes]  # KeyError for a missing angle
+    r_in = spherical.get("r", 1)
+    r_is_tensor = isinstance(r_in, torch.Tensor)
+    tensors = angles_in + ([r_in] if r_is_tensor else [])
+    if c.s_ndim == 0:
+        tensors = [r_in] if r_is_tensor else []
+        if not tensors:
+            raise TypeError("to_cartesian_dot on a 0-angle tree needs a tensor r")
+    device = _require_cuda_tensors(tensors, "to_cartesian_dot")
+    dtype = _compute_dtype(tensors)
+    coef = torch.as_tensor(k, device=device).to(dtype)
+    if coef.dim() not in (1, 2) or coef.shape[-1] != c.c_ndim:
+        raise ValueError(f"k must have shape ({c.c_ndim},) or (m, {c.c_ndim}), got {tuple(coef.shape)}")
+    single = coef.dim() == 1
+    coef = coef.reshape(-1, c.c_ndim).contiguous()
+    m = coef.shape[0]
+    if c.s_ndim == 0:
+        out = coef[:, 0].reshape((m,) + (1,) * r_in.dim()) * r_in.to(dtype)
+        return out[0] if single else out
+    if not r_is_tensor:
+        if isinstance(r_in, complex):
+            raise TypeError("complex r is not supported")
+        r_in = None if r_in == 1 else torch.full((), float(r_in), dtype=dtype, device=device)
+    angles = [a if a.dtype == dtype else a.to(dtype) for a in angles_in]
+    r = None if r_in is None else (r_in if r_in.dtype == dtype else r_in.to(dtype))
+    ct = plan_for(c)
+    full = tuple(torch.broadcast_shapes(*[t.shape for t in angles + ([r] if r is not None else [])]))
+    geo = _Geometry(list(angles) + [r], full)
+    out = torch.empty((m, *full), dtype=dtype, device=device)
+    if geo.n and m:
+        lib = _native.lib()
+        shape_arr = _native.i64_array(geo.shape)
+        mask_arr = _native.u32_array(geo.masks[:-1])
+        ws_ptr, ws_bytes = None, 0
+        if len(geo.shape) > 1 or any(mk != 1 for mk in geo.masks[:-1]):
+            ws_bytes = int(
+                lib.us_to_cartesian_workspace_bytes(C.byref(ct.plan), _DTYPE_CODE[dtype], geo.n, len(geo.shape), shape_arr, mask_arr)
+            )
+            if ws_bytes:
+                ws = _workspace_for(device, ws_bytes)
+                ws_ptr, ws_bytes = ws.data_ptr(), ws.numel()
+        with device_guard(device):
+            status = lib.us_to_cartesian_dot(
+                C.byref(ct.plan),
+                _DTYPE_CODE[dtype],
+                geo.n,
+                len(geo.shape),
+                shape_arr,
+                _native.void_p_array([t.data_ptr() for t in geo.tensors[:-1]]),
+                mask_arr,
+                _ptr(geo.tensors[-1]),
+                geo.masks[-1],
+                coef.data_ptr(),
+                m,
+                out.data_ptr(),
+                ws_ptr,
+                ws_bytes,
+                _stream_ptr(device),
+            )
+        _native.check(status, "us_to_cartesian_dot")
+    return out[0] if single else out
+
+
 # --------------------------------------------------------------------------------------
 # from_cartesian
 # --------------------------------------------------------------------------------------

@@ -148,6 +148,39 @@ extern "C" int us_to_cartesian_ws(const us_plan_t* plan, int dtype, int64_t n, i
   return launch_to_cartesian_strided(p, dtype, st);
 }
 
+extern "C" int us_to_cartesian_dot(const us_plan_t* plan, int dtype, int64_t n, int ndim, const int64_t* shape,
+                                   const void* const* angle_dev, const uint32_t* angle_mask, const void* r_dev,
+                                   uint32_t r_mask, const void* coef_dev, int m, void* out_dev, void* workspace_dev,
+                                   int64_t workspace_bytes, void* stream) {
+  static const char* who = "us_to_cartesian_dot";
+  XformParams p;
+  memset(&p, 0, sizeof p);
+  if (int rc = fill_common(p, plan, dtype, n, ndim, shape, who)) return rc;
+  if (!angle_dev || !angle_mask) return fail(US_EINVAL, "%s: null pointer table", who);
+  if (m < 0) return fail(US_EINVAL, "%s: m < 0", who);
+  if (m == 0 || n == 0) return 0;
+  if (!coef_dev || !out_dev) return fail(US_EINVAL, "%s: null coefficient or output pointer", who);
+  for (int s = 0; s < plan->n_nodes; ++s) {
+    if (!angle_dev[s]) return fail(US_EINVAL, "%s: angle %d is null", who, s);
+    p.in[s] = angle_dev[s];
+    p.in_mask[s] = angle_mask[s];
+  }
+  p.r_in = r_dev;
+  p.r_mask = r_mask;
+  p.dot_coef = coef_dev;
+  p.dot_out = out_dev;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = try_launch_to_cartesian_bcast(p, dtype, workspace_dev, workspace_bytes, st, m);
+  if (rc != kNotTaken) return rc;
+  const size_t esz = dtype == US_F32 ? 4 : 8;
+  for (int j = 0; j < m; ++j) {
+    p.dot_coef = (const char*)coef_dev + (size_t)j * plan->n_leaves * esz;
+    p.dot_out = (char*)out_dev + (size_t)j * n * esz;
+    if ((rc = launch_to_cartesian_strided(p, dtype, st)) != 0) return rc;
+  }
+  return 0;
+}
+
 extern "C" int us_to_cartesian(const us_plan_t* plan, int dtype, int64_t n, int ndim, const int64_t* shape,
                                const void* const* angle_dev, const uint32_t* angle_mask, const void* r_dev,
                                uint32_t r_mask, void* const* out_dev, void* stream) {

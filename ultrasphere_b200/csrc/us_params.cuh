@@ -19,6 +19,9 @@ struct XformParams {
   int32_t ndim;
   int64_t n;
   int64_t shape[US_MAX_DIMS];
+  // to, linear-functional variant (us_to_cartesian_dot): out[g] = sum_l dot_coef[l] * x_l[g]
+  const void* dot_coef;  // n_leaves device values, c_nodes order; nullptr => ordinary to_cartesian
+  void* dot_out;         // n elements
 };
 static_assert(sizeof(XformParams) < 32000, "kernel parameter block must fit the 32 KB limit");
 
@@ -28,7 +31,8 @@ int launch_jacobian_strided(const XformParams& p, const int32_t* cos_pow, const 
 
 // broadcast path of to_cartesian (us_transform_bcast.cu): sincos tables for broadcast angles
 int64_t bcast_workspace_bytes(const us_plan_t* plan, int dtype, int64_t n, int ndim, const int64_t* shape, const uint32_t* angle_mask);
-int try_launch_to_cartesian_bcast(XformParams& p, int dtype, void* workspace, int64_t workspace_bytes, cudaStream_t st);
+// with p.dot_coef set: `functionals` launches over the same tables, coefficient rows n_leaves apart, output rows n apart
+int try_launch_to_cartesian_bcast(XformParams& p, int dtype, void* workspace, int64_t workspace_bytes, cudaStream_t st, int functionals = 1);
 
 // contiguous fast path (us_transform_tiled.cu); returns 0 if it took the launch, kNotTaken if the
 // caller should use the strided kernels, any other value is an error status

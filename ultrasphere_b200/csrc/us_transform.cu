@@ -49,11 +49,15 @@ struct Indexer {
   }
 };
 
-template <typename T>
+// DOT: the leaf products are not stored but folded into one linear functional sum_l coef[l] * x_l
+// (us_to_cartesian_dot), in program order, one FMA per leaf.
+template <typename T, bool DOT>
 __global__ void __launch_bounds__(256) to_cartesian_strided(const __grid_constant__ XformParams p) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.n) return;
   Indexer ix(p, i);
+  const T* const coef = (const T*)p.dot_coef;
+  T acc = T(0);
   T cur = p.r_in ? ld_stream((const T*)p.r_in + ix.off(p.r_mask)) : T(1);
   T stack[US_MAX_STACK];
   int sp = 0;
@@ -69,18 +73,25 @@ __global__ void __launch_bounds__(256) to_cartesian_strided(const __grid_constan
     const T ps = mul_rn(cur, sv[0]);
     T* oc = nullptr;
     T* os = nullptr;
-    switch (node_kind(w)) {
+    const int kind = node_kind(w);
+    if constexpr (DOT) {
+      if (kind == US_NODE_A || kind == US_NODE_B) acc = fma(__ldg(coef + node_cos_leaf(w)), pc, acc);
+      if (kind == US_NODE_A || kind == US_NODE_BP) acc = fma(__ldg(coef + node_sin_leaf(w)), ps, acc);
+    }
+    switch (kind) {
       case US_NODE_A:
-        oc = (T*)p.out[node_cos_leaf(w)];
-        os = (T*)p.out[node_sin_leaf(w)];
+        if constexpr (!DOT) {
+          oc = (T*)p.out[node_cos_leaf(w)];
+          os = (T*)p.out[node_sin_leaf(w)];
+        }
         if (sp > 0) cur = stack[--sp];
         break;
       case US_NODE_B:
-        oc = (T*)p.out[node_cos_leaf(w)];
+        if constexpr (!DOT) oc = (T*)p.out[node_cos_leaf(w)];
         cur = ps;
         break;
       case US_NODE_BP:
-        os = (T*)p.out[node_sin_leaf(w)];
+        if constexpr (!DOT) os = (T*)p.out[node_sin_leaf(w)];
         cur = pc;
         break;
       default:  // US_NODE_C: defer the sin branch, descend into the cos branch
@@ -91,6 +102,7 @@ __global__ void __launch_bounds__(256) to_cartesian_strided(const __grid_constan
     if (oc) st_stream(oc + i, pc);
     if (os) st_stream(os + i, ps);
   }
+  if constexpr (DOT) st_stream((T*)p.dot_out + i, acc);
 }
 
 template <typename T>
@@ -216,10 +228,15 @@ int launch_to_cartesian_strided(const XformParams& p, int dtype, cudaStream_t st
   const int threads = 256;
   const int64_t blocks = (p.n + threads - 1) / threads;
   if (blocks > 0x7FFFFFFFLL) return fail(US_EINVAL, "us_to_cartesian: n too large for one launch");
-  if (dtype == US_F32)
-    to_cartesian_strided<float><<<(unsigned)blocks, threads, 0, st>>>(p);
+  if (p.dot_coef) {
+    if (dtype == US_F32)
+      to_cartesian_strided<float, true><<<(unsigned)blocks, threads, 0, st>>>(p);
+    else
+      to_cartesian_strided<double, true><<<(unsigned)blocks, threads, 0, st>>>(p);
+  } else if (dtype == US_F32)
+    to_cartesian_strided<float, false><<<(unsigned)blocks, threads, 0, st>>>(p);
   else
-    to_cartesian_strided<double><<<(unsigned)blocks, threads, 0, st>>>(p);
+    to_cartesian_strided<double, false><<<(unsigned)blocks, threads, 0, st>>>(p);
   US_CUDA_TRY(cudaGetLastError(), "to_cartesian_strided launch");
   return 0;
 }

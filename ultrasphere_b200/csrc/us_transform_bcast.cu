@@ -9,6 +9,7 @@
 // once, and the grid kernel is pure table look-up (L1-resident), multiply and 128-bit streaming
 // stores: it is bound by the HBM write of c_ndim * sizeof(T) bytes per grid point.
 #include <mutex>
+#include <string.h>
 
 #include "us_common.cuh"
 #include "us_params.cuh"
@@ -78,7 +79,9 @@ __device__ __forceinline__ uint32_t fast_div(uint32_t n, uint32_t magic, uint32_
 // One thread owns V consecutive grid points (V divides the innermost extent, so they share all
 // outer indices).  Persistent grid-stride loop; grids of < 2^31 points (wider ones take the strided
 // kernel).  MAXD = 4 or 8 keeps the index vector in registers.
-template <typename T, int V, bool STACK, int MAXD>
+// DOT (us_to_cartesian_dot): the leaf products are folded into sum_l coef[l] * x_l instead of being
+// stored, so the kernel writes sizeof(T) instead of c_ndim * sizeof(T) bytes per grid point.
+template <typename T, int V, bool STACK, int MAXD, bool DOT>
 __global__ void __launch_bounds__(256) to_cartesian_bcast(const __grid_constant__ BcastParams bp) {
   const XformParams& p = bp.x;
   const int nd = p.ndim;
@@ -118,6 +121,9 @@ __global__ void __launch_bounds__(256) to_cartesian_bcast(const __grid_constant_
     }
     T stack[STACK ? US_MAX_STACK : 1][V];  // chains (create_standard...) need none
     int sp = 0;
+    T acc[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = T(0);
     for (int k = 0; k < nn; ++k) {
       const uint64_t w = p.plan.node[k];
       const int slot = node_slot(w);
@@ -142,8 +148,21 @@ __global__ void __launch_bounds__(256) to_cartesian_bcast(const __grid_constant_
       mul_vec<V>(cur, cs, pc);
       mul_vec<V>(cur, sn, ps);
       const int kind = node_kind(w);
-      T* const oc = (kind == US_NODE_A || kind == US_NODE_B) ? (T*)p.out[node_cos_leaf(w)] : nullptr;
-      T* const os = (kind == US_NODE_A || kind == US_NODE_BP) ? (T*)p.out[node_sin_leaf(w)] : nullptr;
+      T* const oc = (!DOT && (kind == US_NODE_A || kind == US_NODE_B)) ? (T*)p.out[node_cos_leaf(w)] : nullptr;
+      T* const os = (!DOT && (kind == US_NODE_A || kind == US_NODE_BP)) ? (T*)p.out[node_sin_leaf(w)] : nullptr;
+      if constexpr (DOT) {
+        const T* const coef = (const T*)p.dot_coef;
+        if (kind == US_NODE_A || kind == US_NODE_B) {
+          const T kc = __ldg(coef + node_cos_leaf(w));
+#pragma unroll
+          for (int v = 0; v < V; ++v) acc[v] = fma(kc, pc[v], acc[v]);
+        }
+        if (kind == US_NODE_A || kind == US_NODE_BP) {
+          const T ks = __ldg(coef + node_sin_leaf(w));
+#pragma unroll
+          for (int v = 0; v < V; ++v) acc[v] = fma(ks, ps[v], acc[v]);
+        }
+      }
       if constexpr (STACK) {
         if (kind == US_NODE_C) {
 #pragma unroll
@@ -168,6 +187,167 @@ __global__ void __launch_bounds__(256) to_cartesian_bcast(const __grid_constant_
       }
       if (oc) store_vec<T, V>(oc + g0, tc);
       if (os) store_vec<T, V>(os + g0, ts);
+    }
+    if constexpr (DOT) {
+      BVec<T, V> ta;
+#pragma unroll
+      for (int v = 0; v < V; ++v) ta.v[v] = acc[v];
+      store_vec<T, V>((T*)p.dot_out + g0, ta);
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Row kernel for chain trees (no `c` node: create_standard / standard_prime / spherical / polar) on
+// tensor grids of up to 4 launch dims.  One warp owns one row of the innermost launch dim at a
+// time; the 32 lanes cover the row with 16-byte vectors, U vectors per lane and 512 contiguous
+// bytes per warp instruction.  The outer indices are decomposed once per row, and every node whose
+// angle does not vary along the row — all but one on the grids integrate() builds — is evaluated
+// ONCE per lane as a scalar (one table look-up, two multiplies); only from the first row-varying
+// node on does the lane carry its U*V points.  Everything a node needs sits in one 64-byte
+// descriptor in program order.  Used for the linear functional only (us_to_cartesian_dot): there the
+// generic grid kernel above stays issue-bound on its ~175 instructions of index and parameter
+// arithmetic per point although it writes c_ndim times less, while this one needs ~80 (measured,
+// C5: 0.96 ms -> 0.57 ms).  For the leaf-storing transform both kernels are bound by the same HBM
+// writes and the generic one, with its higher occupancy, is the faster (1.02 vs 1.09 ms under ncu).
+struct RowNode {
+  const void* tab;   // (sin, cos) table of the angle, or nullptr: evaluate from `in`
+  const void* in;
+  uint32_t stride[4];  // element stride of the operand along the launch dims (right-aligned; [3] = along the row)
+  uint32_t kind, leaf_c, leaf_s, pad;  // leaf slots index the coefficients; US_NO_LEAF: none
+  uint64_t pad2[2];                    // 64 bytes
+};
+constexpr int kRowNodes = 64;
+struct RowParams {
+  RowNode node[kRowNodes];
+  const void* r_in;
+  const void* dot_coef;
+  void* dot_out;
+  uint32_t r_stride[4];
+  uint32_t extent[4], magic[4], shift[4];  // launch dims right-aligned: [3] is the row
+  uint32_t n_rows, nn;
+};
+
+template <typename T, int V, int U>
+__global__ void __launch_bounds__(256, 2) to_cartesian_dot_rows(const __grid_constant__ RowParams rp) {
+  constexpr int W = U * V;
+  using P2 = typename Pair<T>::type;
+  const uint32_t E = rp.extent[3], n_rows = rp.n_rows;
+  const int nn = (int)rp.nn;
+  const uint32_t lane = threadIdx.x & 31u, warps = gridDim.x * (blockDim.x >> 5);
+  const T* const coef = (const T*)rp.dot_coef;
+  for (uint32_t row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n_rows; row += warps) {
+    const uint32_t q2 = fast_div(row, rp.magic[2], rp.shift[2]), i2 = row - q2 * rp.extent[2];
+    const uint32_t q1 = fast_div(q2, rp.magic[1], rp.shift[1]), i1 = q2 - q1 * rp.extent[1];
+    const uint32_t i0 = q1;
+    auto offset = [&](const uint32_t (&st)[4]) -> uint32_t { return i0 * st[0] + i1 * st[1] + i2 * st[2]; };
+    const uint32_t g_row = row * E;
+    for (uint32_t c0 = 0; c0 < E; c0 += 32u * W) {
+      uint32_t col[U];
+      bool ok[U];
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        col[j] = c0 + ((uint32_t)j * 32u + lane) * V;
+        ok[j] = col[j] < E;
+      }
+      bool uni = true;  // the running product (and the functional) is still the same for the whole row
+      T cur_s = T(1), acc_s = T(0);
+      T cur_v[W], acc_v[W];
+      if (rp.r_in) {
+        const uint32_t o = offset(rp.r_stride);
+        if (rp.r_stride[3] == 0) {
+          cur_s = __ldg((const T*)rp.r_in + o);
+        } else {
+          uni = false;
+#pragma unroll
+          for (int j = 0; j < U; ++j)
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+              cur_v[j * V + v] = ok[j] ? __ldg((const T*)rp.r_in + o + col[j] + v) : T(0);
+              acc_v[j * V + v] = T(0);
+            }
+        }
+      }
+      for (int k = 0; k < nn; ++k) {
+        const RowNode& nk = rp.node[k];
+        const uint32_t o = offset(nk.stride);
+        const bool row_varying = nk.stride[3] != 0;
+        const bool to_sin = nk.kind == US_NODE_B;  // the chain continues through the sin child
+        const P2* const tb = (const P2*)nk.tab;
+        T s0 = T(0), c0v = T(1);
+        if (!row_varying) {
+          if (tb) {
+            const P2 sc = __ldg(tb + o);
+            s0 = sc.x;
+            c0v = sc.y;
+          } else {
+            const T th[1] = {__ldg((const T*)nk.in + o)};
+            T s1[1], c1[1];
+            sincos_vec<1>(th, s1, c1);
+            s0 = s1[0];
+            c0v = c1[0];
+          }
+        }
+        T kc = T(0), ks = T(0);
+        if (nk.leaf_c != US_NO_LEAF) kc = __ldg(coef + nk.leaf_c);
+        if (nk.leaf_s != US_NO_LEAF) ks = __ldg(coef + nk.leaf_s);
+        if (!row_varying && uni) {
+          const T pc = mul_rn(cur_s, c0v), ps = mul_rn(cur_s, s0);
+          if (nk.leaf_c != US_NO_LEAF) acc_s = fma(kc, pc, acc_s);
+          if (nk.leaf_s != US_NO_LEAF) acc_s = fma(ks, ps, acc_s);
+          cur_s = to_sin ? ps : pc;
+          continue;
+        }
+        if (uni) {  // first node that differs along the row: the lane starts carrying its points
+          uni = false;
+#pragma unroll
+          for (int i = 0; i < W; ++i) {
+            cur_v[i] = cur_s;
+            acc_v[i] = acc_s;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          T sn[V], cs[V];
+          if (!row_varying) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+              sn[v] = s0;
+              cs[v] = c0v;
+            }
+          } else if (tb) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+              P2 sc;
+              sc.x = T(0);
+              sc.y = T(0);
+              if (ok[j]) sc = __ldg(tb + o + col[j] + v);
+              sn[v] = sc.x;
+              cs[v] = sc.y;
+            }
+          } else {
+            T th[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) th[v] = ok[j] ? __ldg((const T*)nk.in + o + col[j] + v) : T(0);
+            sincos_vec<V>(th, sn, cs);
+          }
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            const int i = j * V + v;
+            const T pc = mul_rn(cur_v[i], cs[v]), ps = mul_rn(cur_v[i], sn[v]);
+            if (nk.leaf_c != US_NO_LEAF) acc_v[i] = fma(kc, pc, acc_v[i]);
+            if (nk.leaf_s != US_NO_LEAF) acc_v[i] = fma(ks, ps, acc_v[i]);
+            cur_v[i] = to_sin ? ps : pc;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        BVec<T, V> ta;
+#pragma unroll
+        for (int v = 0; v < V; ++v) ta.v[v] = uni ? acc_s : acc_v[j * V + v];
+        if (ok[j]) store_vec<T, V>((T*)rp.dot_out + g_row + col[j], ta);
+      }
     }
   }
 }
@@ -202,7 +382,10 @@ static void launch_bcast(const BcastParams& bp, cudaStream_t st) {
   const int64_t threads_total = (bp.x.n + V - 1) / V;
   const int64_t want = (threads_total + 255) / 256;
   const int64_t cap = 148 * 16;  // a few waves of resident CTAs; the grid-stride loop covers the rest
-  to_cartesian_bcast<T, V, STACK, MAXD><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(bp);
+  if (bp.x.dot_coef)
+    to_cartesian_bcast<T, V, STACK, MAXD, true><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(bp);
+  else
+    to_cartesian_bcast<T, V, STACK, MAXD, false><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(bp);
 }
 
 template <typename T, int MAXD>
@@ -217,6 +400,23 @@ static void launch_bcast_shape(const BcastParams& bp, bool vec_ok, cudaStream_t 
   }
 }
 
+template <typename T, int U>
+static void launch_rows_u(const RowParams& rp, cudaStream_t st) {
+  constexpr int V = 16 / (int)sizeof(T);
+  const int64_t want = ((int64_t)rp.n_rows + 7) / 8, cap = 148 * 8;  // 8 warps per CTA, grid-stride over rows
+  const unsigned grid = (unsigned)(want < cap ? want : cap);
+  to_cartesian_dot_rows<T, V, U><<<grid, 256, 0, st>>>(rp);
+}
+template <typename T>
+static void launch_rows(const RowParams& rp, cudaStream_t st) {
+  constexpr int V = 16 / (int)sizeof(T);
+  const uint32_t vectors = rp.extent[3] / V;  // per row; 32 * U of them per pass of the warp
+  if (vectors <= 32) launch_rows_u<T, 1>(rp, st);
+  else if (vectors <= 64) launch_rows_u<T, 2>(rp, st);
+  else if (vectors <= 96) launch_rows_u<T, 3>(rp, st);
+  else launch_rows_u<T, 4>(rp, st);
+}
+
 // dense element stride of an operand along every launch dim (0 where broadcast)
 static void operand_strides(uint32_t mask, int ndim, const int64_t* shape, uint32_t (&out)[kBcastDims]) {
   uint32_t mul = 1;
@@ -229,7 +429,8 @@ static void operand_strides(uint32_t mask, int ndim, const int64_t* shape, uint3
   }
 }
 
-int try_launch_to_cartesian_bcast(XformParams& p, int dtype, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+int try_launch_to_cartesian_bcast(XformParams& p, int dtype, void* workspace, int64_t workspace_bytes, cudaStream_t st,
+                                  int functionals) {
   if (!workspace || p.ndim > kBcastDims || p.n >= (int64_t)0x7FFFFFFF) return kNotTaken;
   const int esz = dtype == US_F32 ? 4 : 8;
   const int nn = p.plan.n_nodes;
@@ -269,6 +470,7 @@ int try_launch_to_cartesian_bcast(XformParams& p, int dtype, void* workspace, in
   bool vec_ok = (p.shape[p.ndim - 1] % vmax) == 0;
   for (int l = 0; l < p.plan.n_leaves && vec_ok; ++l)
     if (p.out[l] && (reinterpret_cast<uintptr_t>(p.out[l]) & 15u)) vec_ok = false;
+  if (p.dot_coef && (reinterpret_cast<uintptr_t>(p.dot_out) & 15u)) vec_ok = false;  // rows are n*esz apart: n % vmax == 0
   static BcastParams bp;  // 18 KB: too large for the stack of a deeply nested caller; guarded below
   static std::mutex bp_lock;
   std::lock_guard<std::mutex> guard(bp_lock);
@@ -289,12 +491,52 @@ int try_launch_to_cartesian_bcast(XformParams& p, int dtype, void* workspace, in
     }
   }
   const bool small = p.ndim <= 4;
-  if (dtype == US_F32) {
-    small ? launch_bcast_shape<float, 4>(bp, vec_ok, st) : launch_bcast_shape<float, 8>(bp, vec_ok, st);
-  } else {
-    small ? launch_bcast_shape<double, 4>(bp, vec_ok, st) : launch_bcast_shape<double, 8>(bp, vec_ok, st);
+  // a functional of a chain tree on a grid with long enough rows: the row kernel (see to_cartesian_dot_rows)
+  const int64_t inner = p.shape[p.ndim - 1];
+  const bool rows_ok = p.dot_coef && vec_ok && p.plan.max_stack == 0 && p.ndim >= 2 && p.ndim <= 4 && nn <= kRowNodes && inner * esz >= 256 &&
+                       p.n / inner >= 2 * 148 * 8 && !getenv("US_NO_ROWS");
+  static RowParams rp;  // guarded by bp_lock like bp
+  if (rows_ok) {
+    memset(&rp, 0, sizeof rp);
+    const int shift_d = 4 - p.ndim;  // right-align the launch dims
+    for (int d = 0; d < 4; ++d) {
+      const int src = d - shift_d;
+      rp.extent[d] = src >= 0 ? bp.extent[src] : 1u;
+      rp.magic[d] = src >= 0 ? bp.magic[src] : 0u;
+      rp.shift[d] = src >= 0 ? bp.shift[src] : 0xFFFFFFFFu;
+      rp.r_stride[d] = src >= 0 ? bp.r_stride[src] : 0u;
+    }
+    for (int k = 0; k < nn; ++k) {
+      const uint64_t w = p.plan.node[k];
+      const int slot = node_slot(w), kind = node_kind(w);
+      RowNode& nk = rp.node[k];
+      nk.tab = p.tab[slot];
+      nk.in = p.in[slot];
+      nk.kind = (uint32_t)kind;
+      nk.leaf_c = (kind == US_NODE_A || kind == US_NODE_B) ? (uint32_t)node_cos_leaf(w) : (uint32_t)US_NO_LEAF;
+      nk.leaf_s = (kind == US_NODE_A || kind == US_NODE_BP) ? (uint32_t)node_sin_leaf(w) : (uint32_t)US_NO_LEAF;
+      for (int d = 0; d < 4; ++d) nk.stride[d] = d - shift_d >= 0 ? bp.stride[slot][d - shift_d] : 0u;
+    }
+    rp.r_in = p.r_in;
+    rp.n_rows = (uint32_t)(p.n / inner);
+    rp.nn = (uint32_t)nn;
   }
-  US_CUDA_TRY(cudaGetLastError(), "to_cartesian_bcast launch");
+  for (int j = 0; j < (p.dot_coef ? functionals : 1); ++j) {
+    if (p.dot_coef) {
+      bp.x.dot_coef = (const char*)p.dot_coef + (size_t)j * p.plan.n_leaves * esz;
+      bp.x.dot_out = (char*)p.dot_out + (size_t)j * p.n * esz;
+    }
+    if (rows_ok) {
+      rp.dot_coef = bp.x.dot_coef;
+      rp.dot_out = bp.x.dot_out;
+      dtype == US_F32 ? launch_rows<float>(rp, st) : launch_rows<double>(rp, st);
+    } else if (dtype == US_F32) {
+      small ? launch_bcast_shape<float, 4>(bp, vec_ok, st) : launch_bcast_shape<float, 8>(bp, vec_ok, st);
+    } else {
+      small ? launch_bcast_shape<double, 4>(bp, vec_ok, st) : launch_bcast_shape<double, 8>(bp, vec_ok, st);
+    }
+    US_CUDA_TRY(cudaGetLastError(), "to_cartesian_bcast launch");
+  }
   return 0;
 }
 
