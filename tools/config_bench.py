@@ -55,4 +55,12 @@ for spec, dt, n in CONFIGS:
             "graph_from_frac_hbm": n * bpp / gf / 1e6 / peak, "graph_to_frac_hbm": n * bpp / gt / 1e6 / peak})
     del x, s
     torch.cuda.empty_cache()
+# FP64 / FP32 FMA peaks of this GPU (dependent-free DFMA / FFMA loops on every SM): the denominator of
+# the pipe-bound float64 kernels, which MEASURED_PEAKS.json does not carry
+import ctypes
+from ultrasphere_b200 import _native
+for code, name in ((1, "fp64"), (0, "fp32")):
+    tf = ctypes.c_double()
+    _native.check(_native.lib().us_probe_fma_peak(code, 4096, ctypes.byref(tf)), "probe")
+    out[f"measured_fma_peak_{name}_tflops"] = tf.value
 print(json.dumps(out, indent=1))
