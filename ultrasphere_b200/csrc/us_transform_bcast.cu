@@ -228,28 +228,38 @@ struct RowParams {
   uint32_t n_rows, nn;
 };
 
-template <typename T, int V, int U>
-__global__ void __launch_bounds__(256, 2) to_cartesian_dot_rows(const __grid_constant__ RowParams rp) {
+// NN > 0: the node count is a compile-time constant and the node loop is fully unrolled, so every
+// descriptor field becomes a direct constant-bank operand, the per-node tests are hoisted out of
+// the row loop and the coefficients are loaded once per thread (short chains: the trees
+// integrate() is used with); NN = 0: run-time loop.
+template <typename T, int V, int U, int NN>
+__global__ void __launch_bounds__(256, 3) to_cartesian_dot_rows(const __grid_constant__ RowParams rp) {
   constexpr int W = U * V;
+  constexpr int KC = NN ? NN : 1;
   using P2 = typename Pair<T>::type;
   const uint32_t E = rp.extent[3], n_rows = rp.n_rows;
-  const int nn = (int)rp.nn;
-  const uint32_t lane = threadIdx.x & 31u, warps = gridDim.x * (blockDim.x >> 5);
+  const int nn = NN ? NN : (int)rp.nn;
+  const uint32_t lane_col = (threadIdx.x & 31u) * V, warps = gridDim.x * (blockDim.x >> 5);
+  const uint32_t first_row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const T* const coef = (const T*)rp.dot_coef;
-  for (uint32_t row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n_rows; row += warps) {
-    const uint32_t q2 = fast_div(row, rp.magic[2], rp.shift[2]), i2 = row - q2 * rp.extent[2];
-    const uint32_t q1 = fast_div(q2, rp.magic[1], rp.shift[1]), i1 = q2 - q1 * rp.extent[1];
-    const uint32_t i0 = q1;
-    auto offset = [&](const uint32_t (&st)[4]) -> uint32_t { return i0 * st[0] + i1 * st[1] + i2 * st[2]; };
-    const uint32_t g_row = row * E;
-    for (uint32_t c0 = 0; c0 < E; c0 += 32u * W) {
-      uint32_t col[U];
-      bool ok[U];
+  T kc_all[KC], ks_all[KC];  // coefficients of the leaves each node produces (0: no such leaf)
+  if constexpr (NN > 0) {
 #pragma unroll
-      for (int j = 0; j < U; ++j) {
-        col[j] = c0 + ((uint32_t)j * 32u + lane) * V;
-        ok[j] = col[j] < E;
-      }
+    for (int k = 0; k < NN; ++k) {
+      kc_all[k] = rp.node[k].leaf_c != US_NO_LEAF ? __ldg(coef + rp.node[k].leaf_c) : T(0);
+      ks_all[k] = rp.node[k].leaf_s != US_NO_LEAF ? __ldg(coef + rp.node[k].leaf_s) : T(0);
+    }
+  }
+  for (uint32_t c0 = 0; c0 < E; c0 += 32u * W) {  // one pass for rows of up to 32*U*V points
+    const uint32_t col0 = c0 + lane_col;          // this lane's vector j starts at col0 + j*32*V
+    bool ok[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) ok[j] = col0 + (uint32_t)j * 32u * V < E;
+    for (uint32_t row = first_row; row < n_rows; row += warps) {
+      const uint32_t q2 = fast_div(row, rp.magic[2], rp.shift[2]), i2 = row - q2 * rp.extent[2];
+      const uint32_t q1 = fast_div(q2, rp.magic[1], rp.shift[1]), i1 = q2 - q1 * rp.extent[1];
+      const uint32_t i0 = q1;
+      auto offset = [&](const uint32_t (&st)[4]) -> uint32_t { return i0 * st[0] + i1 * st[1] + i2 * st[2]; };
       bool uni = true;  // the running product (and the functional) is still the same for the whole row
       T cur_s = T(1), acc_s = T(0);
       T cur_v[W], acc_v[W];
@@ -259,23 +269,39 @@ __global__ void __launch_bounds__(256, 2) to_cartesian_dot_rows(const __grid_con
           cur_s = __ldg((const T*)rp.r_in + o);
         } else {
           uni = false;
+          const T* const base = (const T*)rp.r_in + o + col0;
 #pragma unroll
           for (int j = 0; j < U; ++j)
 #pragma unroll
             for (int v = 0; v < V; ++v) {
-              cur_v[j * V + v] = ok[j] ? __ldg((const T*)rp.r_in + o + col[j] + v) : T(0);
+              cur_v[j * V + v] = ok[j] ? __ldg(base + j * 32 * V + v) : T(0);
               acc_v[j * V + v] = T(0);
             }
         }
       }
+#pragma unroll(NN ? NN : 1)
       for (int k = 0; k < nn; ++k) {
         const RowNode& nk = rp.node[k];
         const uint32_t o = offset(nk.stride);
         const bool row_varying = nk.stride[3] != 0;
         const bool to_sin = nk.kind == US_NODE_B;  // the chain continues through the sin child
         const P2* const tb = (const P2*)nk.tab;
-        T s0 = T(0), c0v = T(1);
+        T kc, ks;
+        if constexpr (NN > 0) {
+          kc = kc_all[k];
+          ks = ks_all[k];
+        } else {
+          kc = nk.leaf_c != US_NO_LEAF ? __ldg(coef + nk.leaf_c) : T(0);
+          ks = nk.leaf_s != US_NO_LEAF ? __ldg(coef + nk.leaf_s) : T(0);
+        }
+        // one step for one point: a zero coefficient adds an exact zero, so no leaf test is needed
+        auto step = [&](T& cur, T& acc, T sn, T cs) {
+          const T pc = mul_rn(cur, cs), ps = mul_rn(cur, sn);
+          acc = fma(ks, ps, fma(kc, pc, acc));
+          cur = to_sin ? ps : pc;
+        };
         if (!row_varying) {
+          T s0, c0v;
           if (tb) {
             const P2 sc = __ldg(tb + o);
             s0 = sc.x;
@@ -287,15 +313,12 @@ __global__ void __launch_bounds__(256, 2) to_cartesian_dot_rows(const __grid_con
             s0 = s1[0];
             c0v = c1[0];
           }
-        }
-        T kc = T(0), ks = T(0);
-        if (nk.leaf_c != US_NO_LEAF) kc = __ldg(coef + nk.leaf_c);
-        if (nk.leaf_s != US_NO_LEAF) ks = __ldg(coef + nk.leaf_s);
-        if (!row_varying && uni) {
-          const T pc = mul_rn(cur_s, c0v), ps = mul_rn(cur_s, s0);
-          if (nk.leaf_c != US_NO_LEAF) acc_s = fma(kc, pc, acc_s);
-          if (nk.leaf_s != US_NO_LEAF) acc_s = fma(ks, ps, acc_s);
-          cur_s = to_sin ? ps : pc;
+          if (uni) {
+            step(cur_s, acc_s, s0, c0v);
+          } else {
+#pragma unroll
+            for (int i = 0; i < W; ++i) step(cur_v[i], acc_v[i], s0, c0v);
+          }
           continue;
         }
         if (uni) {  // first node that differs along the row: the lane starts carrying its points
@@ -306,47 +329,38 @@ __global__ void __launch_bounds__(256, 2) to_cartesian_dot_rows(const __grid_con
             acc_v[i] = acc_s;
           }
         }
+        if (tb) {
+          const P2* const base = tb + o + col0;
 #pragma unroll
-        for (int j = 0; j < U; ++j) {
-          T sn[V], cs[V];
-          if (!row_varying) {
-#pragma unroll
-            for (int v = 0; v < V; ++v) {
-              sn[v] = s0;
-              cs[v] = c0v;
-            }
-          } else if (tb) {
+          for (int j = 0; j < U; ++j) {
+            if (!ok[j]) continue;
 #pragma unroll
             for (int v = 0; v < V; ++v) {
-              P2 sc;
-              sc.x = T(0);
-              sc.y = T(0);
-              if (ok[j]) sc = __ldg(tb + o + col[j] + v);
-              sn[v] = sc.x;
-              cs[v] = sc.y;
+              const P2 sc = __ldg(base + j * 32 * V + v);
+              step(cur_v[j * V + v], acc_v[j * V + v], sc.x, sc.y);
             }
-          } else {
-            T th[V];
-#pragma unroll
-            for (int v = 0; v < V; ++v) th[v] = ok[j] ? __ldg((const T*)nk.in + o + col[j] + v) : T(0);
-            sincos_vec<V>(th, sn, cs);
           }
+        } else {
+          const T* const base = (const T*)nk.in + o + col0;
 #pragma unroll
-          for (int v = 0; v < V; ++v) {
-            const int i = j * V + v;
-            const T pc = mul_rn(cur_v[i], cs[v]), ps = mul_rn(cur_v[i], sn[v]);
-            if (nk.leaf_c != US_NO_LEAF) acc_v[i] = fma(kc, pc, acc_v[i]);
-            if (nk.leaf_s != US_NO_LEAF) acc_v[i] = fma(ks, ps, acc_v[i]);
-            cur_v[i] = to_sin ? ps : pc;
+          for (int j = 0; j < U; ++j) {
+            if (!ok[j]) continue;
+            T th[V], sn[V], cs[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) th[v] = __ldg(base + j * 32 * V + v);
+            sincos_vec<V>(th, sn, cs);
+#pragma unroll
+            for (int v = 0; v < V; ++v) step(cur_v[j * V + v], acc_v[j * V + v], sn[v], cs[v]);
           }
         }
       }
+      T* const dst = (T*)rp.dot_out + row * E + col0;
 #pragma unroll
       for (int j = 0; j < U; ++j) {
         BVec<T, V> ta;
 #pragma unroll
         for (int v = 0; v < V; ++v) ta.v[v] = uni ? acc_s : acc_v[j * V + v];
-        if (ok[j]) store_vec<T, V>((T*)rp.dot_out + g_row + col[j], ta);
+        if (ok[j]) store_vec<T, V>(dst + j * 32 * V, ta);
       }
     }
   }
@@ -405,7 +419,14 @@ static void launch_rows_u(const RowParams& rp, cudaStream_t st) {
   constexpr int V = 16 / (int)sizeof(T);
   const int64_t want = ((int64_t)rp.n_rows + 7) / 8, cap = 148 * 8;  // 8 warps per CTA, grid-stride over rows
   const unsigned grid = (unsigned)(want < cap ? want : cap);
-  to_cartesian_dot_rows<T, V, U><<<grid, 256, 0, st>>>(rp);
+  switch (rp.nn) {
+    case 2: to_cartesian_dot_rows<T, V, U, 2><<<grid, 256, 0, st>>>(rp); break;
+    case 3: to_cartesian_dot_rows<T, V, U, 3><<<grid, 256, 0, st>>>(rp); break;
+    case 4: to_cartesian_dot_rows<T, V, U, 4><<<grid, 256, 0, st>>>(rp); break;
+    case 5: to_cartesian_dot_rows<T, V, U, 5><<<grid, 256, 0, st>>>(rp); break;
+    case 6: to_cartesian_dot_rows<T, V, U, 6><<<grid, 256, 0, st>>>(rp); break;
+    default: to_cartesian_dot_rows<T, V, U, 0><<<grid, 256, 0, st>>>(rp); break;
+  }
 }
 template <typename T>
 static void launch_rows(const RowParams& rp, cudaStream_t st) {
