@@ -35,6 +35,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// The same on shared-space (32-bit) addresses computed once per kernel: the generic-pointer forms
+// above rebuild the shared window base (S2R CgaCtaId + LEA + ...) at every call site, which the
+// row-ring kernels pay per row and per thread.
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive_s(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
 // global -> shared bulk copy through the TMA unit; bytes % 16 == 0, both addresses 16-byte aligned
 __device__ __forceinline__ void tma_load_row(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
   asm volatile(
@@ -58,6 +77,28 @@ struct alignas(sizeof(T) * V) Vec {
 template <typename T, int V>
 __device__ __forceinline__ Vec<T, V> lds_vec(const T* row, int tid) {
   return *reinterpret_cast<const Vec<T, V>*>(row + tid * V);
+}
+
+// 16-byte (or narrower) load from a shared-space address
+template <typename T, int V>
+__device__ __forceinline__ Vec<T, V> lds_vec_s(uint32_t addr) {
+  Vec<T, V> out;
+  if constexpr (sizeof(T) * V == 16) {
+    uint32_t a, b, c, d;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr));
+    uint32_t w[4] = {a, b, c, d};
+    memcpy(&out, w, 16);
+  } else if constexpr (sizeof(T) * V == 8) {
+    uint32_t a, b;
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(addr));
+    uint32_t w[2] = {a, b};
+    memcpy(&out, w, 8);
+  } else {
+    uint32_t a;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(a) : "r"(addr));
+    memcpy(&out, &a, 4);
+  }
+  return out;
 }
 
 template <typename T, int V>

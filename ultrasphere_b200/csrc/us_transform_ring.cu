@@ -28,22 +28,26 @@ struct RingShared {
   uint64_t empty[kRing];
 };
 
+// Consumer side, on shared-space addresses computed once per thread: `mine` already points at this
+// thread's 16 bytes of slot 0, slots are P*sizeof(T) apart, barriers 8 bytes apart.
 template <typename T, int V>
 struct RingConsumer {
-  const T* rows;
-  RingShared* sh;
+  uint32_t mine, full, empty;
   uint32_t q;
-  int tid;
+  bool lane0;
   static constexpr int P = kRingConsumers * V;
+  __device__ __forceinline__ RingConsumer(const T* rows, RingShared* sh, int tid)
+      : mine(smem_u32(rows) + (uint32_t)tid * V * sizeof(T)), full(smem_u32(&sh->full[0])), empty(smem_u32(&sh->empty[0])),
+        q(0u), lane0((tid & 31) == 0) {}
   __device__ __forceinline__ Vec<T, V> get(int& slot) {
     slot = (int)(q & (kRing - 1));
-    mbar_wait(&sh->full[slot], (q / kRing) & 1u);
+    mbar_wait_s(full + (uint32_t)slot * 8u, (q / kRing) & 1u);
     ++q;
-    return lds_vec<T, V>(rows + (size_t)slot * P, tid);
+    return lds_vec_s<T, V>(mine + (uint32_t)slot * (uint32_t)(P * sizeof(T)));
   }
   __device__ __forceinline__ void release(int slot) {
     __syncwarp();
-    if ((tid & 31) == 0) mbar_arrive(&sh->empty[slot]);
+    if (lane0) mbar_arrive_s(empty + (uint32_t)slot * 8u);
   }
 };
 
@@ -96,7 +100,7 @@ __global__ void __launch_bounds__(kRingBlock, 3) to_cartesian_ring(const __grid_
     }
     return;
   }
-  RingConsumer<T, V> ring{rows, sh, 0u, tid};
+  RingConsumer<T, V> ring(rows, sh, tid);
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t g = tile * P + (int64_t)tid * V;
     Vec<T, V> cur;
@@ -168,7 +172,7 @@ __global__ void __launch_bounds__(kRingBlock, 3) from_cartesian_ring(const __gri
     }
     return;
   }
-  RingConsumer<T, V> ring{rows, sh, 0u, tid};
+  RingConsumer<T, V> ring(rows, sh, tid);
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t g = tile * P + (int64_t)tid * V;
     if (r_out) {
