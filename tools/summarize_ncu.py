@@ -6,7 +6,7 @@ R = sys.argv[1] if len(sys.argv) > 1 else "r01"
 REPORTS = [
     (f"prof_{R}_hopf3_f64", "create_hopf(3) float64, 32 M points (128 B/point/direction: 4.10 GB algorithmic per launch)", 32e6 * 128),
     (f"prof_{R}_ring", "create_random(32, default_rng(0)) float32, 16 M points, ring kernels (264 B/point/direction: 4.22 GB)", 16e6 * 264),
-    (f"prof_{R}_c5", "integrate C5 pieces: broadcast grid kernel (6.79 GB written) and TMA-streamed reduction (1.36 GB read)", None),
+    (f"prof_{R}_c5", "integrate C5 pieces: broadcast grid kernel (6.79 GB written), row kernel of the fused functional (1.36 GB written) and TMA-streamed reduction (1.36 GB read)", None),
 ]
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
