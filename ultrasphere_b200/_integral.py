@@ -246,6 +246,34 @@ def _as_supported(val: torch.Tensor, wdtype: torch.dtype) -> torch.Tensor:
     return val if val.dtype == target else val.to(target)
 
 
+class _WeightedReduceFn(torch.autograd.Function):
+    """Autograd wrapper of the fused contraction: it is linear in ``val`` with real weights, so the
+    backward pass is the outer product of the weights times the incoming gradient (plain torch
+    broadcasting — gradients are not the hot path).  Lets integrals be differentiated with respect
+    to parameters of the integrand."""
+
+    @staticmethod
+    def forward(ctx: Any, val: torch.Tensor, *weights: torch.Tensor) -> torch.Tensor:
+        ctx.save_for_backward(*weights)
+        ctx.val_shape = tuple(val.shape)
+        ctx.val_dtype = val.dtype
+        return _weighted_reduce(val.detach(), [w.detach() for w in weights], out=None)
+
+    @staticmethod
+    def backward(ctx: Any, grad_out: torch.Tensor) -> Any:
+        weights = ctx.saved_tensors
+        k = len(weights)
+        grad = grad_out.reshape((1,) * k + tuple(grad_out.shape))
+        for i, w in enumerate(weights):
+            shape = [1] * len(ctx.val_shape)
+            shape[i] = w.numel()
+            grad = grad * w.reshape(shape).to(grad_out.real.dtype if grad_out.is_complex() else grad_out.dtype)
+        grad = grad.expand(ctx.val_shape)
+        if not ctx.val_dtype.is_complex and grad.is_complex():
+            grad = grad.real
+        return (grad.to(ctx.val_dtype), *([None] * k))
+
+
 def weighted_reduce(
     val: torch.Tensor,
     weights: list[torch.Tensor],
@@ -255,8 +283,20 @@ def weighted_reduce(
     """``sum over the leading len(weights) axes of prod_i w_i[idx_i] * val`` in one fused pass.
 
     ``val``: ``(e_0, …, e_{k-1}, *u)`` on a CUDA device with ``e_i == len(w_i)``; returns shape ``u``.
-    With ``out`` given the result is accumulated into it (used for slab-wise evaluation).
+    With ``out`` given the result is accumulated into it (used for slab-wise evaluation) and ``out``
+    is returned — except when ``val`` carries an autograd graph: then the sum is returned as a new
+    tensor (``out + result``) so that the graph survives.
     """
+    if torch.is_grad_enabled():
+        if any(w.requires_grad for w in weights):
+            raise RuntimeError("weighted_reduce: gradients with respect to the quadrature weights are not provided")
+        if val.requires_grad:
+            res = _WeightedReduceFn.apply(val, *weights)
+            return res if out is None else out + res
+    return _weighted_reduce(val, weights, out=out)
+
+
+def _weighted_reduce(val: torch.Tensor, weights: list[torch.Tensor], *, out: torch.Tensor | None) -> torch.Tensor:
     k = len(weights)
     device = val.device
     val = _as_supported(val, weights[0].dtype)
@@ -313,6 +353,9 @@ def weighted_reduce(
 
 def separable_reduce(vals: list[torch.Tensor], weights: list[torch.Tensor]) -> list[torch.Tensor]:
     """``[sum_j w_a[j] * val_a[j, ...] for a]`` in one launch (all axes share a dtype class)."""
+    if torch.is_grad_enabled() and any(v.requires_grad for v in vals):
+        # the per-axis sum is the one-axis case of the fused contraction, which carries autograd
+        return [weighted_reduce(v, [w]) for v, w in zip(vals, weights)]
     device = vals[0].device
     prepared = []
     outs: list[torch.Tensor] = []
@@ -498,13 +541,10 @@ def integrate(
             # f does not depend on the leading angle: one evaluation, weight = sum of this
             # rank's share of the rule
             part = _contract_dense(c, val, [_sum_weight(w_list[0][lo_rank:hi_rank])] + w_list[1:], None)
-            out = part if out is None else out.add_(part)
+            out = part if out is None else out + part
             break
         part_w = [w_list[0][lo:hi]] + w_list[1:]
-        if out is None:
-            out = _contract_dense(c, val, part_w, None)
-        else:
-            _contract_dense(c, val, part_w, out)
+        out = _contract_dense(c, val, part_w, out)  # accumulates in place (new tensor under autograd)
         lo = hi
     if out is None:  # a rank with an empty share
         probe = f({k: (v[:2] if k == nodes[0] else v) for k, v in xs.items()})
@@ -520,6 +560,9 @@ def shard_rows(n_rows: int, rank: int, world: int) -> tuple[int, int]:
 def _finish(result: torch.Tensor, group: Any | None, *, sharded: bool) -> torch.Tensor:
     if sharded:
         import torch.distributed as dist
+
+        if result.requires_grad:
+            raise RuntimeError("integrate(group=...): the all-reduce of a sharded integral is not differentiable; reduce the gradients yourself")
 
         dist.all_reduce(result, op=dist.ReduceOp.SUM, group=group)
     return result

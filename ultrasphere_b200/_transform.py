@@ -33,6 +33,11 @@ def _require_cuda_tensors(values: Sequence[Any], what: str) -> torch.device:
             raise RuntimeError(
                 f"{what}: tensor on {v.device}; ultrasphere_b200 runs on CUDA devices only (no CPU fallback)"
             )
+        if v.requires_grad and torch.is_grad_enabled():
+            raise RuntimeError(
+                f"{what}: an input requires grad, but the CUDA kernels have no backward pass; "
+                "call under torch.no_grad() or detach() the inputs (silently dropping the graph would be worse)"
+            )
         if device is None:
             device = v.device
         elif v.device != device:
@@ -258,6 +263,7 @@ def _to_cartesian_dense(
             or t.shape != shape
             or t.device != device
             or not t.is_contiguous()
+            or (t.requires_grad and torch.is_grad_enabled())
         ):
             return None
     ct = plan_for(c)
@@ -430,6 +436,7 @@ def _from_cartesian_dense(c: SphericalCoordinates[Any, Any], cartesian: Any) -> 
             or x.shape[0] != len(ct_nodes)
             or not x.is_contiguous()
             or not c.is_c_keys_sorted_range
+            or (x.requires_grad and torch.is_grad_enabled())
         ):
             return None
         dtype, shape, device = x.dtype, x.shape[1:], x.device
@@ -452,6 +459,7 @@ def _from_cartesian_dense(c: SphericalCoordinates[Any, Any], cartesian: Any) -> 
                 or t.shape != shape
                 or t.device != device
                 or not t.is_contiguous()
+                or (t.requires_grad and torch.is_grad_enabled())
             ):
                 return None
         n = first.numel()
