@@ -192,6 +192,26 @@ US_API int us_to_cartesian_dot(const us_plan_t* plan, int dtype, int64_t n, int 
                                void* workspace_dev, int64_t workspace_bytes, void* stream);
 
 /*
+ * ---- backward passes, for torch.autograd ----
+ * The reference is differentiable because it is made of array-API calls
+ * (src/ultrasphere/_coordinates.py:555-579, 636-656); these two entry points give the CUDA path the
+ * same property.  Dense operands only: every array has n elements (the host broadcasts before the
+ * call and autograd sums afterwards).  NULL gradient inputs mean zero.
+ *
+ * us_to_cartesian_backward:  given dL/dx_l (c_nodes order) returns dL/dtheta_s (s_nodes order, all
+ *   n_nodes buffers required) and, if grad_r_dev is not NULL, dL/dr.  r_dev NULL = radius 1.
+ * us_from_cartesian_backward: given dL/dr and dL/dtheta_s returns dL/dx_l (c_nodes order).
+ *   scratch_dev: 2 * n_nodes * n elements of the compute dtype.  Points whose subtree norm is zero
+ *   (no direction) get a zero gradient.
+ */
+US_API int us_to_cartesian_backward(const us_plan_t* plan, int dtype, int64_t n, const void* const* angle_dev,
+                                    const void* r_dev, const void* const* grad_leaf_dev,
+                                    void* const* grad_angle_dev, void* grad_r_dev, void* stream);
+US_API int us_from_cartesian_backward(const us_plan_t* plan, int dtype, int64_t n, const void* const* x_dev,
+                                      const void* grad_r_dev, const void* const* grad_angle_dev,
+                                      void* const* grad_x_dev, void* scratch_dev, void* stream);
+
+/*
  * ---- "next" row: SphericalCoordinates.jacobian (_coordinates.py:668-702) ----
  * out = r * prod over internal nodes of cos(theta)^cos_pow * sin(theta)^sin_pow, one fused pass that
  * shares the sincos with nothing else to write: (s_ndim + 2) * sizeof(T) bytes per point.  The

@@ -323,20 +323,3 @@ def test_integrals_differentiate_with_respect_to_integrand_parameters(slab):
     total = sum(v.sum() for v in sep.values())
     (g2,) = torch.autograd.grad(total, a)
     assert abs(g2.item() - 2 * total.item() / 0.7) <= 1e-10 * abs(g2.item())
-
-
-def test_transforms_refuse_inputs_that_require_grad():
-    c = us.create_spherical()
-    x = torch.rand((3, 100), device=DEV, requires_grad=True)
-    with pytest.raises(RuntimeError, match="no backward"):
-        c.from_cartesian(x)
-    with pytest.raises(RuntimeError, match="no backward"):
-        c.from_cartesian({i: x[i] for i in range(3)})
-    with torch.no_grad():
-        s = c.from_cartesian(x)
-    th = {key: v.clone().requires_grad_() for key, v in s.items()}
-    for call in (lambda: c.to_cartesian(th), lambda: c.to_cartesian(th, as_array=True), lambda: c.to_cartesian_dot(th, [1.0, 2.0, 3.0]), lambda: c.jacobian(th)):
-        with pytest.raises(RuntimeError, match="no backward"):
-            call()
-    with torch.no_grad():
-        assert torch.allclose(c.to_cartesian(th, as_array=True), x, atol=1e-5)

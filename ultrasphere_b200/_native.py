@@ -87,6 +87,11 @@ _SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
         [C.POINTER(UsPlan), C.c_int, C.c_int64, C.c_int, _PI64, _PP, C.POINTER(C.c_uint32), C.c_void_p, C.c_uint32,
          C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p],
     ),
+    "us_to_cartesian_backward": (C.c_int, [C.POINTER(UsPlan), C.c_int, C.c_int64, _PP, C.c_void_p, _PP, _PP, C.c_void_p, C.c_void_p]),
+    "us_from_cartesian_backward": (
+        C.c_int,
+        [C.POINTER(UsPlan), C.c_int, C.c_int64, _PP, C.c_void_p, _PP, _PP, C.c_void_p, C.c_void_p],
+    ),
     "us_quadrature_rules": (
         C.c_int,
         [C.c_int, C.POINTER(C.c_uint8), _PI64, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32), _PP, _PP, C.c_void_p],

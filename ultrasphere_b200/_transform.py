@@ -21,7 +21,11 @@ from ._plan import CompiledTree, plan_for
 _DTYPE_CODE = {torch.float32: _native.US_F32, torch.float64: _native.US_F64}
 
 
-def _require_cuda_tensors(values: Sequence[Any], what: str) -> torch.device:
+def _needs_grad(values: Sequence[Any]) -> bool:
+    return torch.is_grad_enabled() and any(isinstance(v, torch.Tensor) and v.requires_grad for v in values)
+
+
+def _require_cuda_tensors(values: Sequence[Any], what: str, *, allow_grad: bool = False) -> torch.device:
     device: torch.device | None = None
     for v in values:
         if not isinstance(v, torch.Tensor):
@@ -33,7 +37,7 @@ def _require_cuda_tensors(values: Sequence[Any], what: str) -> torch.device:
             raise RuntimeError(
                 f"{what}: tensor on {v.device}; ultrasphere_b200 runs on CUDA devices only (no CPU fallback)"
             )
-        if v.requires_grad and torch.is_grad_enabled():
+        if not allow_grad and v.requires_grad and torch.is_grad_enabled():
             raise RuntimeError(
                 f"{what}: an input requires grad, but the CUDA kernels have no backward pass; "
                 "call under torch.no_grad() or detach() the inputs (silently dropping the graph would be worse)"
@@ -186,11 +190,137 @@ def _ptr(t: torch.Tensor | None) -> int | None:
 
 
 # --------------------------------------------------------------------------------------
+# autograd: dense forward launches + the backward kernels (us_*_backward)
+# --------------------------------------------------------------------------------------
+def _rows(t: torch.Tensor, count: int) -> Any:
+    step = (t.numel() // count) * t.element_size() if count else 0
+    return _native.void_p_array([t.data_ptr() + i * step for i in range(count)])
+
+
+class _ToCartesianFn(torch.autograd.Function):
+    """``(c_ndim, *shape)`` from dense equal-shape angles (s_nodes order) and an optional r."""
+
+    @staticmethod
+    def forward(ctx: Any, c: Any, has_r: bool, *ops: torch.Tensor) -> torch.Tensor:
+        ct = plan_for(c)
+        angles, r = (ops[:-1], ops[-1]) if has_r else (ops, None)
+        first = angles[0]
+        n = first.numel()
+        out = torch.empty((ct.n_leaves, *first.shape), dtype=first.dtype, device=first.device)
+        if n:
+            with device_guard(first.device):
+                status = _native.lib().us_to_cartesian(
+                    C.byref(ct.plan), _DTYPE_CODE[first.dtype], n, 1, _native.i64_array([n]),
+                    _native.void_p_array([a.data_ptr() for a in angles]), _native.u32_array([1] * ct.n_nodes),
+                    _ptr(r), 1, _rows(out, ct.n_leaves), _stream_ptr(first.device),
+                )
+            _native.check(status, "us_to_cartesian")
+        ctx.save_for_backward(*ops)
+        ctx.c, ctx.has_r = c, has_r
+        return out
+
+    @staticmethod
+    def backward(ctx: Any, grad_out: torch.Tensor) -> Any:
+        ops = ctx.saved_tensors
+        ct = plan_for(ctx.c)
+        angles, r = (ops[:-1], ops[-1]) if ctx.has_r else (ops, None)
+        first = angles[0]
+        n = first.numel()
+        g = grad_out.contiguous()
+        grad_angles = torch.empty((ct.n_nodes, *first.shape), dtype=first.dtype, device=first.device)
+        grad_r = torch.empty_like(first) if ctx.has_r else None
+        if n:
+            with device_guard(first.device):
+                status = _native.lib().us_to_cartesian_backward(
+                    C.byref(ct.plan), _DTYPE_CODE[first.dtype], n, _native.void_p_array([a.data_ptr() for a in angles]),
+                    _ptr(r), _rows(g, ct.n_leaves), _rows(grad_angles, ct.n_nodes), _ptr(grad_r), _stream_ptr(first.device),
+                )
+            _native.check(status, "us_to_cartesian_backward")
+        grads = list(grad_angles.unbind(0)) + ([grad_r] if ctx.has_r else [])
+        return (None, None, *grads)
+
+
+class _FromCartesianFn(torch.autograd.Function):
+    """``(1 + s_ndim, *shape)`` — r, then the angles in s_nodes order — from dense equal-shape leaves."""
+
+    @staticmethod
+    def forward(ctx: Any, c: Any, *leaves: torch.Tensor) -> torch.Tensor:
+        ct = plan_for(c)
+        first = leaves[0]
+        n = first.numel()
+        out = torch.empty((1 + ct.n_nodes, *first.shape), dtype=first.dtype, device=first.device)
+        if n:
+            rows = _rows(out, 1 + ct.n_nodes)
+            with device_guard(first.device):
+                status = _native.lib().us_from_cartesian(
+                    C.byref(ct.plan), _DTYPE_CODE[first.dtype], n, 1, _native.i64_array([n]),
+                    _native.void_p_array([x.data_ptr() for x in leaves]), _native.u32_array([1] * ct.n_leaves),
+                    rows[0], _native.void_p_array([rows[1 + s] for s in range(ct.n_nodes)]), _stream_ptr(first.device),
+                )
+            _native.check(status, "us_from_cartesian")
+        ctx.save_for_backward(*leaves)
+        ctx.c = c
+        return out
+
+    @staticmethod
+    def backward(ctx: Any, grad_out: torch.Tensor) -> Any:
+        leaves = ctx.saved_tensors
+        ct = plan_for(ctx.c)
+        first = leaves[0]
+        n = first.numel()
+        g = grad_out.contiguous()
+        grad_x = torch.empty((ct.n_leaves, *first.shape), dtype=first.dtype, device=first.device)
+        if n:
+            scratch = torch.empty((2 * ct.n_nodes, n), dtype=first.dtype, device=first.device)
+            rows = _rows(g, 1 + ct.n_nodes)
+            with device_guard(first.device):
+                status = _native.lib().us_from_cartesian_backward(
+                    C.byref(ct.plan), _DTYPE_CODE[first.dtype], n, _native.void_p_array([x.data_ptr() for x in leaves]),
+                    rows[0], _native.void_p_array([rows[1 + s] for s in range(ct.n_nodes)]), _rows(grad_x, ct.n_leaves),
+                    scratch.data_ptr(), _stream_ptr(first.device),
+                )
+            _native.check(status, "us_from_cartesian_backward")
+        return (None, *grad_x.unbind(0))
+
+
+def _dense_operands(tensors: list[torch.Tensor], dtype: torch.dtype) -> list[torch.Tensor]:
+    """Broadcast to one shape with differentiable torch ops: autograd sums the gradients back."""
+    full = torch.broadcast_shapes(*[t.shape for t in tensors])
+    return [t.to(dtype).expand(full).contiguous() for t in tensors]
+
+
+def _to_cartesian_with_grad(c: SphericalCoordinates[Any, Any], angles_in: list[Any], r_in: Any, as_array: bool) -> Any:
+    r_is_tensor = isinstance(r_in, torch.Tensor)
+    tensors = angles_in + ([r_in] if r_is_tensor else [])
+    device = _require_cuda_tensors(tensors, "to_cartesian", allow_grad=True)
+    dtype = _compute_dtype(tensors)
+    if not r_is_tensor and r_in != 1:
+        tensors = tensors + [torch.full((), float(r_in), dtype=dtype, device=device)]
+    has_r = len(tensors) > len(angles_in)
+    out = _ToCartesianFn.apply(c, has_r, *_dense_operands(tensors, dtype))
+    return out if as_array else dict(zip(c.c_nodes, out.unbind(0)))
+
+
+def _from_cartesian_with_grad(c: SphericalCoordinates[Any, Any], leaves_in: list[Any]) -> dict[Any, Any]:
+    _require_cuda_tensors(leaves_in, "from_cartesian", allow_grad=True)
+    dtype = _compute_dtype(leaves_in)
+    out = _FromCartesianFn.apply(c, *_dense_operands(leaves_in, dtype))
+    rows = out.unbind(0)
+    result: dict[Any, Any] = {"r": rows[0]}
+    for s in range(c.s_ndim - 1, -1, -1):
+        result[c.s_nodes[s]] = rows[1 + s]
+    return result
+
+
+# --------------------------------------------------------------------------------------
 # to_cartesian
 # --------------------------------------------------------------------------------------
 def to_cartesian(c: SphericalCoordinates[Any, Any], spherical: Mapping[Any, Any], *, as_array: bool = False) -> Any:
     angles_in = [spherical[k] for k in c.s_nodes]  # KeyError for a missing angle
     r_in = spherical.get("r", 1)
+    if c.s_ndim > 0 and _needs_grad(angles_in + [r_in]):
+        # differentiable path: every entry has the full broadcast shape (values as in the reference)
+        return _to_cartesian_with_grad(c, angles_in, r_in, as_array)
     if c.s_ndim == 0:
         # a single leaf that is also the root: x = r  (SURVEY.md App. A.5)
         if as_array:
@@ -361,6 +491,13 @@ def to_cartesian_dot(c: SphericalCoordinates[Any, Any], spherical: Mapping[Any, 
     angles_in = [spherical[key] for key in c.s_nodes]  # KeyError for a missing angle
     r_in = spherical.get("r", 1)
     r_is_tensor = isinstance(r_in, torch.Tensor)
+    if c.s_ndim > 0 and _needs_grad(angles_in + [r_in] + [k]):
+        # under autograd: the contraction of the differentiable transform (gradients are not the hot path)
+        x = to_cartesian(c, spherical, as_array=True)
+        coef = torch.as_tensor(k, device=x.device).to(x.dtype)
+        if coef.dim() not in (1, 2) or coef.shape[-1] != c.c_ndim:
+            raise ValueError(f"k must have shape ({c.c_ndim},) or (m, {c.c_ndim}), got {tuple(coef.shape)}")
+        return torch.einsum("v,v...->..." if coef.dim() == 1 else "mv,v...->m...", coef, x)
     tensors = angles_in + ([r_in] if r_is_tensor else [])
     if c.s_ndim == 0:
         tensors = [r_in] if r_is_tensor else []
@@ -502,6 +639,8 @@ def from_cartesian(c: SphericalCoordinates[Any, Any], cartesian: Any) -> dict[An
     leaves_in = [cartesian[k] for k in c.c_nodes]  # mapping, or a tensor indexed by leaf id
     if c.s_ndim == 0:
         return {"r": leaves_in[0]}
+    if _needs_grad(leaves_in):
+        return _from_cartesian_with_grad(c, leaves_in)
     device = _require_cuda_tensors(leaves_in, "from_cartesian")
     dtype = _compute_dtype(leaves_in)
     leaves = [x if x.dtype == dtype else x.to(dtype) for x in leaves_in]
