@@ -414,17 +414,29 @@ def _device_rules(
 ) -> tuple[dict[Any, torch.Tensor], dict[Any, torch.Tensor]]:
     """Quadrature tables of ``c`` on ``device``, kept on the coordinate object between calls (the
     H2D copies of the tables are synchronous pageable copies, ~20 us each).  The integrand receives
-    copies of the angle tensors, so an in-place edit cannot poison the cache."""
+    COPIES of the angle tensors, so an in-place edit cannot poison the cache; the angles of one
+    dtype are cached as one flat tensor so that the copy is one launch, not ``s_ndim``."""
     cache = c.__dict__.setdefault("_quad_cache", {})
     key = (n, dtype, device, expand, _rule_backend)
     hit = cache.get(key)
     if hit is None:
         if len(cache) >= 16:
             cache.clear()
-        hit = roots(c, n, device=device, dtype=dtype, expand_dims_x=expand, xp=xp)
+        xs, ws = roots(c, n, device=device, dtype=dtype, expand_dims_x=expand, xp=xp)
+        pools: dict[torch.dtype, list[Any]] = {}
+        layout = []
+        for node, x in xs.items():
+            members = pools.setdefault(x.dtype, [])
+            at = sum(m.numel() for m in members)
+            members.append(x.reshape(-1))
+            layout.append((node, x.dtype, at, x.numel(), tuple(x.shape)))
+        flat = {dt: torch.cat(members) for dt, members in pools.items()}
+        hit = (flat, layout, ws)
         cache[key] = hit
-    xs, ws = hit
-    return {k: v.clone() for k, v in xs.items()}, ws
+    flat, layout, ws = hit
+    fresh = {dt: t.clone() for dt, t in flat.items()}
+    return {node: fresh[dt][at : at + count].view(shape) for node, dt, at, count, shape in layout}, ws
+
 
 def _sum_weight(w: torch.Tensor) -> torch.Tensor:
     """1-element weight table for an axis the integrand is constant along (sum of the rule)."""

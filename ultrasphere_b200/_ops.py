@@ -22,6 +22,7 @@ import torch
 
 from ._coordinates import SphericalCoordinates
 from ._plan import CompiledTree, plan_for
+from ._transform import broadcast_shapes
 
 _plans: dict[int, CompiledTree] = {}
 _handles: "weakref.WeakKeyDictionary[Any, int]" = weakref.WeakKeyDictionary()
@@ -56,7 +57,7 @@ def to_cartesian_op(angles: list[torch.Tensor], r: torch.Tensor | None, plan: in
     dtype = _compute_dtype(ops)
     ang = [a if a.dtype == dtype else a.to(dtype) for a in angles]
     rr = None if r is None else (r if r.dtype == dtype else r.to(dtype))
-    full = tuple(torch.broadcast_shapes(*[t.shape for t in ops]))
+    full = tuple(broadcast_shapes(*[t.shape for t in ops]))
     return _launch_to(ct, angles[0].device, dtype, ang, rr, full, list(range(ct.n_leaves)))
 
 
@@ -67,7 +68,7 @@ def _(angles: list[torch.Tensor], r: torch.Tensor | None, plan: int) -> torch.Te
     dtype = ops[0].dtype
     for t in ops[1:]:
         dtype = torch.promote_types(dtype, t.dtype)
-    full = torch.broadcast_shapes(*[t.shape for t in ops])
+    full = broadcast_shapes(*[t.shape for t in ops])
     return angles[0].new_empty((ct.n_leaves, *full), dtype=dtype)
 
 
@@ -81,7 +82,7 @@ def from_cartesian_op(leaves: list[torch.Tensor], plan: int) -> torch.Tensor:
         raise ValueError(f"expected {ct.n_leaves} leaf tensors, got {len(leaves)}")
     dtype = _compute_dtype(leaves)
     xs = [x if x.dtype == dtype else x.to(dtype) for x in leaves]
-    full = tuple(torch.broadcast_shapes(*[t.shape for t in xs]))
+    full = tuple(broadcast_shapes(*[t.shape for t in xs]))
     return _launch_from(ct, leaves[0].device, dtype, xs, full, True, list(range(ct.n_nodes)))
 
 
@@ -91,7 +92,7 @@ def _(leaves: list[torch.Tensor], plan: int) -> torch.Tensor:
     dtype = leaves[0].dtype
     for t in leaves[1:]:
         dtype = torch.promote_types(dtype, t.dtype)
-    full = torch.broadcast_shapes(*[t.shape for t in leaves])
+    full = broadcast_shapes(*[t.shape for t in leaves])
     return leaves[0].new_empty((ct.n_nodes + 1, *full), dtype=dtype)
 
 

@@ -50,6 +50,26 @@ def _require_cuda_tensors(values: Sequence[Any], what: str, *, allow_grad: bool 
     return device
 
 
+def broadcast_shapes(*shapes: Sequence[int]) -> tuple[int, ...]:
+    """NumPy broadcasting of plain integer shapes.  ``torch.broadcast_shapes`` goes through the
+    symbolic-shape machinery and costs ~35 us for five operands; this costs ~2."""
+    nd = 0
+    for sh in shapes:
+        if len(sh) > nd:
+            nd = len(sh)
+    out = [1] * nd
+    for sh in shapes:
+        off = nd - len(sh)
+        for i, e in enumerate(sh):
+            if e != 1:
+                j = off + i
+                if out[j] == 1:
+                    out[j] = e
+                elif out[j] != e:
+                    raise RuntimeError(f"shapes {[tuple(x) for x in shapes]} are not broadcastable")
+    return tuple(out)
+
+
 def _compute_dtype(tensors: Sequence[torch.Tensor]) -> torch.dtype:
     dt = tensors[0].dtype
     for t in tensors[1:]:
@@ -148,7 +168,14 @@ def _span_of(t: torch.Tensor, nd: int) -> tuple[torch.Tensor, list[bool]]:
     raise AssertionError("contiguous tensor must be dense")
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream_ptr(device: torch.device) -> int:
+    """``cudaStream_t`` of the caller's current stream on ``device`` (the raw getter skips building a
+    ``torch.cuda.Stream`` object: 0.3 us instead of 3)."""
+    if _raw_stream is not None:
+        return int(_raw_stream(device.index if device.index is not None else torch.cuda.current_device()))
     return torch.cuda.current_stream(device).cuda_stream
 
 
@@ -285,7 +312,7 @@ class _FromCartesianFn(torch.autograd.Function):
 
 def _dense_operands(tensors: list[torch.Tensor], dtype: torch.dtype) -> list[torch.Tensor]:
     """Broadcast to one shape with differentiable torch ops: autograd sums the gradients back."""
-    full = torch.broadcast_shapes(*[t.shape for t in tensors])
+    full = broadcast_shapes(*[t.shape for t in tensors])
     return [t.to(dtype).expand(full).contiguous() for t in tensors]
 
 
@@ -349,14 +376,14 @@ def to_cartesian(c: SphericalCoordinates[Any, Any], spherical: Mapping[Any, Any]
     shapes = [tuple(a.shape) for a in angles]
     same = all(s == shapes[0] for s in shapes) and (r is None or r_shape == shapes[0] or r_shape == ())
     if same or as_array:
-        full = shapes[0] if same else torch.broadcast_shapes(r_shape, *shapes)
+        full = shapes[0] if same else broadcast_shapes(r_shape, *shapes)
         out = _launch_to(ct, device, dtype, angles, r, full, list(range(ct.n_leaves)))
         if as_array:
             return out
         return {leaf: out[i] for i, leaf in enumerate(c.c_nodes)}
     # heterogeneous shapes: every leaf keeps the broadcast shape of r and its own ancestors
     leaf_shapes = [
-        torch.broadcast_shapes(r_shape, *[shapes[a] for a in ct.leaf_ancestors[l]]) for l in range(ct.n_leaves)
+        broadcast_shapes(r_shape, *[shapes[a] for a in ct.leaf_ancestors[l]]) for l in range(ct.n_leaves)
     ]
     result: dict[int, torch.Tensor] = {}
     for shape in dict.fromkeys(leaf_shapes):
@@ -521,7 +548,7 @@ def to_cartesian_dot(c: SphericalCoordinates[Any, Any], spherical: Mapping[Any, 
     angles = [a if a.dtype == dtype else a.to(dtype) for a in angles_in]
     r = None if r_in is None else (r_in if r_in.dtype == dtype else r_in.to(dtype))
     ct = plan_for(c)
-    full = tuple(torch.broadcast_shapes(*[t.shape for t in angles + ([r] if r is not None else [])]))
+    full = tuple(broadcast_shapes(*[t.shape for t in angles + ([r] if r is not None else [])]))
     geo = _Geometry(list(angles) + [r], full)
     out = torch.empty((m, *full), dtype=dtype, device=device)
     if geo.n and m:
@@ -653,8 +680,8 @@ def from_cartesian(c: SphericalCoordinates[Any, Any], cartesian: Any) -> dict[An
         for s in order:
             result[c.s_nodes[s]] = out[1 + s]
         return result
-    full = tuple(torch.broadcast_shapes(*shapes))
-    node_shapes = [tuple(torch.broadcast_shapes(*[shapes[l] for l in ct.angle_leaves[s]])) for s in range(ct.n_nodes)]
+    full = tuple(broadcast_shapes(*shapes))
+    node_shapes = [tuple(broadcast_shapes(*[shapes[l] for l in ct.angle_leaves[s]])) for s in range(ct.n_nodes)]
     got: dict[int, torch.Tensor] = {}
     r_out: torch.Tensor | None = None
     for shape in dict.fromkeys([full] + node_shapes):
@@ -743,7 +770,7 @@ def jacobian(c: SphericalCoordinates[Any, Any], spherical: Mapping[Any, Any]) ->
         for kind, out in (("cos", cos_pow), ("sin", sin_pow)):
             child = get_child(c.G, node, kind)
             out.append(0 if c.G.out_degree(child) == 0 else int(c.S[child]) + 1)
-    full = tuple(torch.broadcast_shapes(*[t.shape for t in angles + ([r] if r is not None else [])]))
+    full = tuple(broadcast_shapes(*[t.shape for t in angles + ([r] if r is not None else [])]))
     geo = _Geometry(list(angles) + [r], full)
     out = torch.empty(full, dtype=dtype, device=device)
     if geo.n == 0:
