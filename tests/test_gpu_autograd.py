@@ -111,7 +111,7 @@ def test_round_trip_gradient_is_the_identity_and_broadcast_inputs_sum():
         assert torch.allclose(g, wv, rtol=1e-12, atol=1e-12)
 
 
-def test_float32_gradients_dot_and_what_still_refuses():
+def test_float32_gradients_dot_and_jacobian():
     c = us.create_spherical()
     x = torch.rand((3, 1000), device=DEV, requires_grad=True)
     s = c.from_cartesian(x)
@@ -127,7 +127,9 @@ def test_float32_gradients_dot_and_what_still_refuses():
     xs = c.to_cartesian({kk: v.detach() for kk, v in th.items()}, as_array=True)
     assert torch.allclose(k.grad, xs.sum(dim=1), rtol=1e-12)
     assert all(v.grad is not None for v in th.values())
-    with pytest.raises(RuntimeError, match="no backward"):
-        c.jacobian(th)
+    jac = c.jacobian(th)  # under autograd: the same product in torch ops
+    with torch.no_grad():
+        fused = c.jacobian(th)
+    assert jac.requires_grad and torch.allclose(jac, fused, rtol=1e-13)
     with torch.no_grad():
         assert not c.from_cartesian(x)["r"].requires_grad

@@ -243,3 +243,21 @@ def test_custom_ops_trace_without_a_gpu():
         assert torch.ops.ultrasphere_b200.weighted_reduce(v, w).shape == (3,)
     with pytest.raises(NotImplementedError):
         torch.ops.ultrasphere_b200.from_cartesian([torch.zeros(3) for _ in range(4)], h)
+
+
+def test_plain_integer_broadcast_shapes_matches_torch():
+    import random
+
+    from ultrasphere_b200._transform import broadcast_shapes
+
+    rnd = random.Random(0)
+    for _ in range(500):
+        nd = rnd.randint(0, 4)
+        base = [rnd.choice([0, 1, 2, 3, 5]) for _ in range(nd)]
+        shapes = []
+        for _ in range(rnd.randint(1, 5)):
+            d = rnd.randint(0, nd)
+            shapes.append(tuple(rnd.choice([1, base[nd - d + i]]) for i in range(d)))
+        assert broadcast_shapes(*shapes) == tuple(torch.broadcast_shapes(*shapes)), shapes
+    with pytest.raises(RuntimeError):
+        broadcast_shapes((2, 3), (4, 3))

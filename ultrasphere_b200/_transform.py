@@ -758,6 +758,18 @@ def jacobian(c: SphericalCoordinates[Any, Any], spherical: Mapping[Any, Any]) ->
         return r_in
     r_is_tensor = isinstance(r_in, torch.Tensor)
     tensors = angles_in + ([r_in] if r_is_tensor else [])
+    cos_pow, sin_pow = [], []
+    for node in c.s_nodes:
+        for kind, out in (("cos", cos_pow), ("sin", sin_pow)):
+            child = get_child(c.G, node, kind)
+            out.append(0 if c.G.out_degree(child) == 0 else int(c.S[child]) + 1)
+    if _needs_grad(tensors):
+        # under autograd the product is spelled in torch ops (gradients are not the hot path)
+        _require_cuda_tensors(tensors, "jacobian", allow_grad=True)
+        val = r_in
+        for a, cp, sp in zip(angles_in, cos_pow, sin_pow):
+            val = val * torch.cos(a) ** cp * torch.sin(a) ** sp
+        return val
     device = _require_cuda_tensors(tensors, "jacobian")
     dtype = _compute_dtype(tensors)
     if not r_is_tensor:
@@ -765,11 +777,6 @@ def jacobian(c: SphericalCoordinates[Any, Any], spherical: Mapping[Any, Any]) ->
     angles = [a if a.dtype == dtype else a.to(dtype) for a in angles_in]
     r = None if r_in is None else (r_in if r_in.dtype == dtype else r_in.to(dtype))
     ct = plan_for(c)
-    cos_pow, sin_pow = [], []
-    for node in c.s_nodes:
-        for kind, out in (("cos", cos_pow), ("sin", sin_pow)):
-            child = get_child(c.G, node, kind)
-            out.append(0 if c.G.out_degree(child) == 0 else int(c.S[child]) + 1)
     full = tuple(broadcast_shapes(*[t.shape for t in angles + ([r] if r is not None else [])]))
     geo = _Geometry(list(angles) + [r], full)
     out = torch.empty(full, dtype=dtype, device=device)
