@@ -19,7 +19,10 @@ US_MAX_RULE_POINTS = 2048
 US_F32, US_F64 = 0, 1
 US_ABI_VERSION = 1
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libultrasphere_b200.so")
+# ULTRASPHERE_B200_LIB=<path>: load another build of the library (A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("ULTRASPHERE_B200_LIB") or os.path.join(
+    os.path.dirname(os.path.abspath(__file__)), "lib", "libultrasphere_b200.so"
+)
 
 
 class UsPlan(C.Structure):
