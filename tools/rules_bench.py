@@ -71,4 +71,20 @@ for backend in ("scipy", "device"):
     for _ in range(5):
         t0 = time.perf_counter(); vals = sweep(backend); torch.cuda.synchronize(); best = min(best, time.perf_counter() - t0)
     out[f"integrate_sweep|standard:4|n6..29|{backend}"] = {"us_per_integral": best * 1e6 / len(ns), "last": vals[-1].item()}
+# one small integral (n = 16, fused integrand): eager call against CUDA-graph replay
+kk = torch.tensor(np.random.default_rng(0).uniform(0, 1, 5), device=dev)
+small = lambda: us.integrate(c, lambda s: torch.exp(c.to_cartesian_dot(s, kk)), False, 16, xp=torch, device=dev, dtype=torch.float64)
+small(); torch.cuda.synchronize()
+side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
+with torch.cuda.stream(side):
+    small()
+torch.cuda.current_stream().wait_stream(side)
+g = torch.cuda.CUDAGraph()
+with torch.cuda.graph(g):
+    res = small()
+def many(fn, reps=200):
+    fn(); torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(reps): fn()
+    torch.cuda.synchronize(); return (time.perf_counter() - t0) / reps * 1e6
+out["integrate_small|standard:4|n16|fused"] = {"eager_us": many(small), "graph_replay_us": many(g.replay), "value": res.item()}
 print(json.dumps(out, indent=1))
