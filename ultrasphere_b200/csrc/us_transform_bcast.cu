@@ -8,6 +8,10 @@
 // DFMA-class instructions each).  Here a pre-pass tabulates (sin, cos) of every broadcast angle
 // once, and the grid kernel is pure table look-up (L1-resident), multiply and 128-bit streaming
 // stores: it is bound by the HBM write of c_ndim * sizeof(T) bytes per grid point.
+//
+// The same file holds the linear-functional variants (us_to_cartesian_dot): sum_l k_l * x_l folded
+// into the transform instead of storing the leaves (DOT template flag of the grid kernel, and the
+// warp-per-row kernel to_cartesian_dot_rows for chain trees).
 #include <mutex>
 #include <string.h>
 
