@@ -261,3 +261,24 @@ def test_plain_integer_broadcast_shapes_matches_torch():
         assert broadcast_shapes(*shapes) == tuple(torch.broadcast_shapes(*shapes)), shapes
     with pytest.raises(RuntimeError):
         broadcast_shapes((2, 3), (4, 3))
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/ultrasphere_b200.h compiles as C99 and a C program can drive the library."""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    _native.lib()  # make sure the library exists (conftest builds it when missing)
+    exe = tmp_path / "abi_check"
+    subprocess.run(
+        ["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(root, "include"),
+         os.path.join(root, "tests", "c_abi", "abi_check.c"), "-o", str(exe),
+         "-L", os.path.dirname(_native.LIB_PATH), "-lultrasphere_b200", f"-Wl,-rpath,{os.path.dirname(_native.LIB_PATH)}"],
+        check=True,
+    )
+    done = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert done.returncode == 0, (done.returncode, done.stdout, done.stderr)
+    assert done.stdout.startswith("abi 1")
