@@ -187,3 +187,15 @@ def test_row_kernel_with_a_dense_angle_and_no_table():
     from tests.test_gpu_parity import assert_leaves_close
 
     assert_leaves_close(host(rows), want, np.ones(1), depth_of(c), "dense angle")
+    # the functional through the row kernel: per-point sincos of the dense angle inside the vector phase
+    k = rng.normal(size=4)
+    drows, dgeneric = _both_kernels(lambda: c.to_cartesian_dot(dict(a_dev), dev(k)))
+    assert torch.equal(drows, dgeneric)
+    assert_dot_close(host(drows), k, want, depth_of(c), "dense angle dot")
+    # ... and with the dense angle at the root, so that every later node is row-uniform in vector mode
+    ang2 = {"theta0": rng.uniform(0, 3, shape), "theta1": rng.uniform(0, 3, (1, 70, 1)), "theta2": rng.uniform(0, 6, (40, 1, 1))}
+    a2 = {key: dev(v) for key, v in ang2.items()}
+    want2 = vo.to_cartesian(t, dict(ang2), as_array=True)
+    d2, g2 = _both_kernels(lambda: c.to_cartesian_dot(dict(a2), dev(k)))
+    assert torch.equal(d2, g2)
+    assert_dot_close(host(d2), k, want2, depth_of(c), "dense root angle dot")
