@@ -11,6 +11,9 @@ POINTS_PER_GPU synthetic points resident in HBM.  Rank 0 prints ONE JSON line.
   roofline   the dominant kernel's algorithmic HBM bytes / its event-timed duration / measured peak
   e2e        the same round trip through the public API from pinned HOST buffers, copies included
   cpu_baseline  the NumPy oracle (port of the reference's path) on this box's host, bounded sample
+  quadrature the other half of BASELINE's metric: us.integrate on create_standard(4), n = 96
+             (170 M nodes, float64), grid sharded over the ranks with one all-reduce; nodes/s for
+             the reference-form integrand and for the fused functional (outside the timed steps)
 
 ``--impl reference`` times the reference's own CPU algorithm (the NumPy port in ``oracle/``; the
 reference is pure Python and cannot travel to the GPU box) on all host cores.
@@ -49,6 +52,7 @@ def parse() -> argparse.Namespace:
     ap.add_argument("--points", type=int, default=POINTS_PER_GPU, help="points per GPU (default: the BASELINE size)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-quadrature", action="store_true", help="skip the integrate() leg (BASELINE configs[4])")
     return ap.parse_args()
 
 
@@ -354,6 +358,58 @@ def run_b200(args: argparse.Namespace, emit) -> None:
             "how": "pinned host dict-of-arrays -> HostPipeline.round_trip (chunked H2D / from_cartesian / to_cartesian / D2H of spherical and Cartesian results on 3 streams), wall clock around the calls, max over ranks",
         }
 
+    # ---- quadrature leg: the second half of the metric (BASELINE.json configs[4]) ----------------
+    # us.integrate on create_standard(4), n = 96 (169,869,312 nodes), float64, f = exp(k.x); the
+    # leading grid axis is sharded over the ranks (strong scaling) with one NCCL all-reduce of the
+    # scalar.  Two integrands: the reference's own form (materialises the Cartesian grid, then
+    # torch.einsum) and the fused functional.  CUDA events, max over ranks.
+    quadrature = None
+    if not args.no_quadrature:
+        try:
+            del x
+        except NameError:
+            pass
+        torch.cuda.empty_cache()
+        import numpy as np
+
+        from scipy.special import iv
+
+        c4 = us.create_standard(4)
+        k5 = np.random.default_rng(0).uniform(0, 1, 5)
+        kd = torch.from_numpy(k5).to(dev)
+        kn = float(np.linalg.norm(k5))
+        want = float((2 * np.pi) ** 2.5 * kn ** (1 - 2.5) * iv(1.5, kn))  # integral of exp(k.x) over S^4, closed form
+        nq = 96
+        nodes = nq * nq * nq * 2 * nq
+        group = dist.group.WORLD if world > 1 else None
+        forms = {
+            "reference_form": lambda sph_: torch.exp(torch.einsum("v,v...->...", kd, c4.to_cartesian(sph_, as_array=True))),
+            "fused_functional": lambda sph_: torch.exp(c4.to_cartesian_dot(sph_, kd)),
+        }
+        quadrature = {"workload": "us.integrate(create_standard(4), exp(k.x), n=96) float64, 169,869,312 nodes",
+                      "scaling": "strong (leading grid axis sharded over the ranks, one all-reduce of the scalar)",
+                      "analytic": want}
+        for name, f in forms.items():
+            run = lambda: us.integrate(c4, f, False, nq, xp=torch, device=dev, dtype=torch.float64, group=group)  # noqa: E731
+            for _ in range(3):
+                got = run()
+            barrier()
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 10
+            q0.record()
+            for _ in range(reps):
+                got = run()
+            q1.record()
+            barrier()
+            ms = torch.tensor([q0.elapsed_time(q1) / reps], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            rel = abs(got.item() - want) / want
+            if not rel <= 1e-12:
+                raise SystemExit(f"bench.py: integral off by {rel} relative — refusing to report a number")
+            quadrature[name] = {"ms_per_integral": float(ms.item()), "nodes_per_s": nodes / (float(ms.item()) * 1e-3), "rel_err_vs_analytic": rel}
+        torch.cuda.empty_cache()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -396,6 +452,7 @@ def run_b200(args: argparse.Namespace, emit) -> None:
             "inputs": "U(-1,1) per leaf, torch.Generator(cuda).manual_seed(1234+rank), resident in HBM",
         },
         "roofline": roofline, "e2e": e2e, "gpu_launches": 2 * args.steps, "clocks": clocks,
+        "quadrature": quadrature,
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_single_core(min(CPU_SAMPLE, n))

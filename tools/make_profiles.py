@@ -24,7 +24,7 @@ for r in rows[1:]:
     if len(r) > vi:
         tot[r[ki]] = tot.get(r[ki], 0) + ms(r); cnt[r[ki]] += 1
 all_ms = sum(tot.values())
-L = [f"# {R} — ncu launch list of `python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline`", "",
+L = [f"# {R} — ncu launch list of `python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-quadrature`", "",
      "`ncu --metrics gpu__time_duration.sum --clock-control none -c 80` (cold-cache, serialised: compare SHARES).", "",
      "| kernel | launches | total ms | share |", "|---|---|---|---|"]
 for k, v in sorted(tot.items(), key=lambda kv: -kv[1]):
@@ -49,7 +49,7 @@ keys = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio"]
 out = [f"# {R} — `ncu --set full --clock-control none` on the two tiled kernels", "",
-       "Command: `ncu --set full --clock-control none --import-source on -k regex:cartesian_tiled -s 4 -c 2 python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --points 64000000` "
+       "Command: `ncu --set full --clock-control none --import-source on -k regex:cartesian_tiled -s 4 -c 2 python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-quadrature --points 64000000` "
        "(create_standard(9), float32, 64 M points; algorithmic bytes per launch = 64e6 x 80 B = 5.12 GB). Raw page: `" + f"{R}_ncu_full_raw.csv`.", ""]
 traffic = {}
 for r in rows[2:]:
