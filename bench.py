@@ -223,8 +223,22 @@ def run_reference(args: argparse.Namespace, emit) -> None:
         dt = time.perf_counter() - t0
     value = sample * args.steps / dt
     desc = f"{sample} points per step split over {len(parts)} threads"
+    # quadrature leg on the host: the same integrand on a bounded grid (n = 40: 5.12 M nodes, ~0.5 s)
+    quadrature = None
+    if not args.no_quadrature:
+        t4 = vo.create_standard(4)
+        k5 = np.random.default_rng(0).uniform(0, 1, 5)
+        nq = 40
+        f = lambda s_: np.exp(np.einsum("v,v...->...", k5, vo.to_cartesian(t4, s_, as_array=True)))  # noqa: E731
+        vo.integrate(t4, f, False, 8)
+        q0 = time.perf_counter()
+        got = float(vo.integrate(t4, f, False, nq))
+        qdt = time.perf_counter() - q0
+        nodes = nq * nq * nq * 2 * nq
+        quadrature = {"workload": "integrate(create_standard(4), exp(k.x), n=40) float64 on the host (bounded sample of the n=96 grid)",
+                      "reference_form": {"ms_per_integral": qdt * 1e3, "nodes_per_s": nodes / qdt, "value": got}, "cores": 1}
     emit(json.dumps({
-        "impl": "reference",
+        "impl": "reference", "quadrature": quadrature,
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
