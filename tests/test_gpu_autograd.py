@@ -2,7 +2,6 @@
 the reference is differentiable because it is made of array-API calls; here the gradients come from
 two dedicated kernels and are checked against numerical Jacobians and against a plain-torch
 restatement of the reference's loops (_coordinates.py:555-579, 636-656)."""
-import numpy as np
 import pytest
 import torch
 

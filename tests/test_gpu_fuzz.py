@@ -7,7 +7,6 @@ import torch
 
 import ultrasphere_b200 as us
 from oracle import vks_oracle as vo
-from tests.helpers import make
 from tests.test_gpu_parity import assert_angles_close, assert_leaves_close, depth_of, dev, host
 
 pytestmark = pytest.mark.gpu
