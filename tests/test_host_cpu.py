@@ -282,3 +282,28 @@ def test_header_is_plain_c_and_links(tmp_path):
     done = subprocess.run([str(exe)], capture_output=True, text=True)
     assert done.returncode == 0, (done.returncode, done.stdout, done.stderr)
     assert done.stdout.startswith("abi 1")
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the arm the driver runs next to ours) needs no GPU: exactly one
+    JSON line on stdout with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    done = subprocess.run(
+        [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--points", "60000"],
+        capture_output=True, text=True, cwd=root, timeout=300,
+    )
+    assert done.returncode == 0, done.stderr[-2000:]
+    lines = [l for l in done.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches", "quadrature"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["value"] > 0 and line["gpu_launches"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    assert abs(line["quadrature"]["reference_form"]["value"] - 29.449397825582118) < 1e-9
