@@ -1,0 +1,34 @@
+"""bench.py on a real GPU: ONE JSON line with every key of the contract (a reduced batch keeps it short)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_bench_prints_one_contract_line():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    done = subprocess.run(
+        [sys.executable, os.path.join(root, "bench.py"), "--steps", "3", "--warmup", "3", "--points", "8000000", "--no-cpu-baseline"],
+        capture_output=True, text=True, cwd=root, timeout=900,
+    )
+    assert done.returncode == 0, done.stderr[-3000:]
+    lines = [l for l in done.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    line = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "roofline", "e2e", "gpu_launches", "clocks", "quadrature"):
+        assert key in line, key
+    assert line["n_gpus"] == 1 and line["steps"] == 3 and line["gpu_launches"] == 6 and line["dtype"] == "f32"
+    roof = line["roofline"]
+    assert roof["bound"] == "hbm" and roof["unit"] == "GB/s" and 0 < roof["frac"] < 1.05
+    assert abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-9
+    e2e = line["e2e"]
+    assert e2e["value"] > 0 and e2e["h2d_bytes_per_step"] > 0 and e2e["d2h_bytes_per_step"] > 0 and e2e["value"] < line["value"]
+    assert line["clocks"]["sm_mhz"] > 0
+    quad = line["quadrature"]
+    assert quad["reference_form"]["rel_err_vs_analytic"] <= 1e-12 and quad["fused_functional"]["rel_err_vs_analytic"] <= 1e-12
+    assert quad["fused_functional"]["nodes_per_s"] > quad["reference_form"]["nodes_per_s"] > 0
