@@ -419,8 +419,9 @@ def run_b200(args: argparse.Namespace, emit) -> None:
             if world > 1:
                 dist.all_reduce(ms, op=dist.ReduceOp.MAX)
             rel = abs(got.item() - want) / want
-            if not rel <= 1e-12:
-                raise SystemExit(f"bench.py: integral off by {rel} relative — refusing to report a number")
+            if not rel <= 1e-12:  # the same all-reduced value on every rank: no number for this leg, the line still prints
+                quadrature[name] = {"error": f"integral off by {rel} relative: not reported", "rel_err_vs_analytic": rel}
+                continue
             quadrature[name] = {"ms_per_integral": float(ms.item()), "nodes_per_s": nodes / (float(ms.item()) * 1e-3), "rel_err_vs_analytic": rel}
         torch.cuda.empty_cache()
 
