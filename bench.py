@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Benchmark of the hot path: create_standard(9) (10-D `bbbbbbbba`) float32 round trip
-(from_cartesian → to_cartesian), BASELINE.json configs[1].
+"""Benchmark of the hot path.  Headline: create_standard(9) (10-D `bbbbbbbba`) float32 round trip
+(from_cartesian → to_cartesian), BASELINE.json configs[1]; every other BASELINE config is a leg of
+the same line.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
 
@@ -10,13 +11,20 @@ POINTS_PER_GPU synthetic points resident in HBM.  Rank 0 prints ONE JSON line.
   value      whole-job round-trip points/s, inputs resident in HBM, CUDA-event timed, max over ranks
   roofline   the dominant kernel's algorithmic HBM bytes / its event-timed duration / measured peak
   e2e        the same round trip through the public API from pinned HOST buffers, copies included
-  cpu_baseline  the NumPy oracle (port of the reference's path) on this box's host, bounded sample
-  quadrature the other half of BASELINE's metric: us.integrate on create_standard(4), n = 96
-             (170 M nodes, float64), grid sharded over the ranks with one all-reduce; nodes/s for
-             the reference-form integrand and for the fused functional (outside the timed steps)
+  cpu_baseline  the reference's own code (oracle/_ref, else the NumPy port) on this box's host, one
+             core, bounded sample
+  configs    the other BASELINE configs at their full sizes (per GPU): C1 create_spherical() float64
+             1 M, C3 create_hopf(3) and create_standard_prime(8) float64 128 M, C4 create_random(32)
+             float32 64 M — per direction ms, points/s, fraction of the HBM roofline and, for
+             float64, of the FP64 pipe (DFMA peak measured in the run by us_probe_fma_peak)
+  quadrature BASELINE configs[4]: us.integrate on create_standard(4), n = 96 (170 M nodes, float64),
+             grid sharded over the ranks with one all-reduce; nodes/s for the reference-form
+             integrand and for the fused functional (outside the timed steps)
+  multi_rank_check  (N > 1) sharded integrals against the same integrals computed unsharded
 
-``--impl reference`` times the reference's own CPU algorithm (the NumPy port in ``oracle/``; the
-reference is pure Python and cannot travel to the GPU box) on all host cores.
+``--impl reference`` times the UNMODIFIED reference (the four modules `oracle/make_ref.py` copies
+into the git-ignored `oracle/_ref/`, loaded by `oracle/refload.py`) on all host cores; the NumPy
+port in `oracle/` stands in only where that copy is absent.
 """
 from __future__ import annotations
 
@@ -41,6 +49,15 @@ CPU_SAMPLE = 1 << 23
 METRIC = "round-trip points/s (create_standard(9) float32: from_cartesian then to_cartesian)"
 UNIT = "points/s"
 BYTES_PER_POINT_ONE_WAY = 2 * C_NDIM * 4  # (n_in + n_out) * sizeof(float32)
+L2_BYTES = 126 << 20
+
+# (key, tree spec, dtype name, points per GPU, BASELINE.json config it is)
+LEGS = (
+    ("C1", "spherical", "f64", 1_000_000, "configs[0]: create_spherical() `ba` 3-D float64 round trip, 1 M points"),
+    ("C3_hopf3", "hopf:3", "f64", 128_000_000, "configs[2]: create_hopf(3) `ccaacaa` 8-D float64 round trip, 128 M points"),
+    ("C3_standard_prime8", "standard_prime:8", "f64", 128_000_000, "configs[2]: create_standard_prime(8) 9-D float64 round trip, 128 M points"),
+    ("C4", "random:32:0", "f32", 64_000_000, "configs[3]: create_random(32, rng=default_rng(0)) 33-D float32 round trip, 64 M points"),
+)
 
 
 def parse() -> argparse.Namespace:
@@ -53,7 +70,21 @@ def parse() -> argparse.Namespace:
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-quadrature", action="store_true", help="skip the integrate() leg (BASELINE configs[4])")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C1 / C3 / C4 legs")
+    ap.add_argument("--leg-scale", type=float, default=1.0, help="scale the C3 / C4 leg sizes (tests use a small fraction)")
     return ap.parse_args()
+
+
+def make_tree(us, spec: str):
+    """Coordinate object for a spec string, with any module exposing the reference's create_*."""
+    import numpy as np
+
+    head, *rest = spec.split(":")
+    if head == "random":
+        return us.create_random(int(rest[0]), rng=np.random.default_rng(int(rest[1])))
+    if head in ("polar", "spherical"):
+        return getattr(us, f"create_{head}")()
+    return getattr(us, f"create_{head}")(int(rest[0]))
 
 
 # ----------------------------------------------------------------------------------------------
@@ -71,6 +102,7 @@ class ClockSampler:
     def __init__(self, index: int) -> None:
         self.index = index
         self.samples: list[tuple[float, float, int, float]] = []  # (MHz, W, reason mask, host time)
+        self.mem_mhz: list[tuple[float, float]] = []  # (memory MHz, host time)
         self.window: tuple[float, float] | None = None
         self.max_mhz: float | None = None
         self._stop = threading.Event()
@@ -103,7 +135,9 @@ class ClockSampler:
                             mask = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
                         except Exception:
                             mask = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
-                        self.samples.append((mhz, watts, mask, time.perf_counter()))
+                        now = time.perf_counter()
+                        self.samples.append((mhz, watts, mask, now))
+                        self.mem_mhz.append((float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_MEM)), now))
                     except Exception:
                         pass
                     time.sleep(0.001)
@@ -155,47 +189,103 @@ class ClockSampler:
         mask = 0
         for _, _, m, _ in picked:
             mask |= m
-        return {
+        out = {
             "sm_mhz": hot[len(hot) // 2], "sm_max_mhz": self.max_mhz, "power_w_max": peak_w, "samples": len(picked),
             "scope": scope, "reasons": [name for name, bit in self.REASONS if mask & bit], "source": self._mode,
         }
+        # how the clocks moved THROUGH the timed region (ten evenly spaced samples): a kernel that is
+        # timed for tens of milliseconds settles below its first steps when the power cap bites
+        t_lo, t_hi = picked[0][3], picked[-1][3]
+        mem = [m for m, t in self.mem_mhz if t_lo <= t <= t_hi]
+        if mem:
+            out["mem_mhz"] = sorted(mem)[len(mem) // 2]
+            out["mem_mhz_min"] = min(mem)
+        step = max(1, len(picked) // 10)
+        out["trace"] = {"sm_mhz": [x[0] for x in picked[::step]][:10], "power_w": [round(x[1]) for x in picked[::step]][:10],
+                        "sw_power_cap": [int(bool(x[2] & 0x4)) for x in picked[::step]][:10]}
+        return out
 
 
 # ----------------------------------------------------------------------------------------------
-# CPU legs (oracle port)
+# CPU legs: the unmodified reference (oracle/_ref or the mount) where it can be loaded, else the port
 # ----------------------------------------------------------------------------------------------
-def cpu_round_trip(tree, x) -> None:
-    from oracle import vks_oracle as vo
+class CpuImpl:
+    """The reference's CPU path behind one face: `kind` "reference" = its own unmodified modules
+    (oracle/refload.py), "port" = the NumPy restatement in oracle/vks_oracle.py."""
 
-    sph = vo.from_cartesian(tree, x)
-    vo.to_cartesian(tree, sph, as_array=True)
+    def __init__(self, prefer_reference: bool = True) -> None:
+        self.kind = "port"
+        self.note = "NumPy port of the reference's path (oracle/vks_oracle.py); oracle/_ref is absent"
+        if prefer_reference:
+            try:
+                from oracle import refload
+
+                if refload.available():
+                    self._ref = refload.load()
+                    self.kind = "reference"
+                    self.note = f"unmodified ultrasphere modules from {refload.source_dir()} (oracle/refload.py), NumPy arrays"
+            except Exception as exc:  # a missing dependency of the reference on this box
+                self.note = f"NumPy port (loading the reference failed: {type(exc).__name__}: {exc})"
+        if self.kind == "port":
+            from oracle import vks_oracle
+
+            self._vo = vks_oracle
+
+    def tree(self, spec: str):
+        if self.kind == "reference":
+            return make_tree(self._ref.us, spec)
+        return self._vo.make(spec)
+
+    def round_trip(self, tree, x) -> None:
+        if self.kind == "reference":
+            tree.to_cartesian(tree.from_cartesian(x), as_array=True)
+        else:
+            self._vo.to_cartesian(tree, self._vo.from_cartesian(tree, x), as_array=True)
+
+    def integrate_exp(self, n: int) -> tuple[float, float]:
+        """(value, seconds) of integrate(create_standard(4), exp(k.x), n) in float64."""
+        import numpy as np
+
+        k5 = np.random.default_rng(0).uniform(0, 1, 5)
+        t4 = self.tree("standard:4")
+        if self.kind == "reference":
+            f = lambda s_: np.exp(np.einsum("v,v...->...", k5, t4.to_cartesian(s_, as_array=True)))  # noqa: E731
+            run = lambda m: self._ref.us.integrate(t4, f, False, m, xp=np)  # noqa: E731
+        else:
+            f = lambda s_: np.exp(np.einsum("v,v...->...", k5, self._vo.to_cartesian(t4, s_, as_array=True)))  # noqa: E731
+            run = lambda m: self._vo.integrate(t4, f, False, m)  # noqa: E731
+        run(8)
+        t0 = time.perf_counter()
+        got = float(run(n))
+        return got, time.perf_counter() - t0
 
 
 def cpu_baseline_single_core(sample: int) -> dict:
     import numpy as np
 
-    from oracle import vks_oracle as vo
-
-    tree = vo.create_standard(S_NDIM)
+    impl = CpuImpl()
+    tree = impl.tree(f"standard:{S_NDIM}")
     x = np.random.default_rng(0).uniform(-1, 1, (C_NDIM, sample)).astype(np.float32)
-    cpu_round_trip(tree, x[:, : sample // 8])
+    impl.round_trip(tree, x[:, : sample // 8])
     best = float("inf")
     for _ in range(2):
         t0 = time.perf_counter()
-        cpu_round_trip(tree, x)
+        impl.round_trip(tree, x)
         best = min(best, time.perf_counter() - t0)
     return {
         "value": sample / best,
         "unit": UNIT,
         "cores": 1,
-        "kind": "port",
+        "kind": impl.kind,
         "sample": f"{sample} points of the same workload, best of 2, NumPy ufuncs are single-threaded (host has {os.cpu_count()} cpus)",
+        "what": impl.note,
     }
 
 
 def run_reference(args: argparse.Namespace, emit) -> None:
-    """The reference's CPU algorithm (NumPy port) on every host core: the batch is cut into one
-    slice per thread (NumPy releases the GIL inside ufuncs)."""
+    """The reference's CPU implementation on every host core: the batch is cut into one slice per
+    thread and each thread calls the reference's own from_cartesian / to_cartesian on its slice
+    (NumPy releases the GIL inside ufuncs; the reference itself is single-threaded)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -203,17 +293,16 @@ def run_reference(args: argparse.Namespace, emit) -> None:
 
     import numpy as np
 
-    from oracle import vks_oracle as vo
-
+    impl = CpuImpl()
     cores = os.cpu_count() or 1
-    tree = vo.create_standard(S_NDIM)
+    tree = impl.tree(f"standard:{S_NDIM}")
     sample = min(args.points, CPU_SAMPLE)
     x = np.random.default_rng(0).uniform(-1, 1, (C_NDIM, sample)).astype(np.float32)
     bounds = np.linspace(0, sample, cores + 1).astype(int)
     parts = [np.ascontiguousarray(x[:, lo:hi]) for lo, hi in zip(bounds[:-1], bounds[1:]) if hi > lo]
     with ThreadPoolExecutor(max_workers=cores) as pool:
         def step() -> None:
-            list(pool.map(lambda part: cpu_round_trip(tree, part), parts))
+            list(pool.map(lambda part: impl.round_trip(tree, part), parts))
 
         for _ in range(args.warmup):
             step()
@@ -222,29 +311,39 @@ def run_reference(args: argparse.Namespace, emit) -> None:
             step()
         dt = time.perf_counter() - t0
     value = sample * args.steps / dt
+    # the stock call: one thread, the whole sample in one from_cartesian / to_cartesian pair
+    t0 = time.perf_counter()
+    impl.round_trip(tree, x)
+    single = sample / (time.perf_counter() - t0)
     desc = f"{sample} points per step split over {len(parts)} threads"
     # quadrature leg on the host: the same integrand on a bounded grid (n = 40: 5.12 M nodes, ~0.5 s)
     quadrature = None
     if not args.no_quadrature:
-        t4 = vo.create_standard(4)
-        k5 = np.random.default_rng(0).uniform(0, 1, 5)
         nq = 40
-        f = lambda s_: np.exp(np.einsum("v,v...->...", k5, vo.to_cartesian(t4, s_, as_array=True)))  # noqa: E731
-        vo.integrate(t4, f, False, 8)
-        q0 = time.perf_counter()
-        got = float(vo.integrate(t4, f, False, nq))
-        qdt = time.perf_counter() - q0
+        got, qdt = impl.integrate_exp(nq)
         nodes = nq * nq * nq * 2 * nq
         quadrature = {"workload": "integrate(create_standard(4), exp(k.x), n=40) float64 on the host (bounded sample of the n=96 grid)",
-                      "reference_form": {"ms_per_integral": qdt * 1e3, "nodes_per_s": nodes / qdt, "value": got}, "cores": 1}
+                      "reference_form": {"ms_per_integral": qdt * 1e3, "nodes_per_s": nodes / qdt, "value": got}, "cores": 1, "kind": impl.kind}
+    port = None
+    if impl.kind == "reference" and not args.no_cpu_baseline:
+        # second key: the NumPy port of the same path, threaded the same way (the r01 reference arm)
+        pimpl = CpuImpl(prefer_reference=False)
+        ptree = pimpl.tree(f"standard:{S_NDIM}")
+        with ThreadPoolExecutor(max_workers=cores) as pool:
+            list(pool.map(lambda part: pimpl.round_trip(ptree, part), parts))
+            t0 = time.perf_counter()
+            list(pool.map(lambda part: pimpl.round_trip(ptree, part), parts))
+            port = {"value": sample / (time.perf_counter() - t0), "unit": UNIT, "cores": cores, "kind": "port", "sample": desc + ", one step"}
     emit(json.dumps({
         "impl": "reference", "quadrature": quadrature,
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "create_standard(9) bbbbbbbba float32 round trip", "points_per_step": sample,
-                   "runs_on": "host CPU (NumPy port of the reference's path; the Python reference cannot travel to the GPU box)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "config": {"workload": "create_standard(9) bbbbbbbba float32 round trip (BASELINE.json configs[1])", "points_per_step": sample,
+                   "runs_on": f"host CPU, {impl.note}"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": impl.kind, "sample": desc,
+                         "single_thread": {"value": single, "unit": UNIT, "cores": 1, "sample": f"{sample} points, one stock call pair"}},
+        "port": port,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -253,11 +352,22 @@ def run_reference(args: argparse.Namespace, emit) -> None:
 # ----------------------------------------------------------------------------------------------
 # B200 arm
 # ----------------------------------------------------------------------------------------------
+def fp64_instr_per_point(s_ndim: int, c_ndim: int) -> dict:
+    """FP64-pipe instructions (DFMA/DMUL/DADD/DSETP) per point of the float64 kernels, counted in
+    the source (us_common.cuh) and confirmed by ncu's sm__inst_executed_pipe_fp64:
+    from_cartesian 38 per node (atan2 27 + sqrt 8 + norm 3) plus r (c_ndim squares, c_ndim - 1 adds,
+    sqrt ~10); to_cartesian 33 per node (sincos 31 + two products)."""
+    return {"from": 38 * s_ndim + 2 * c_ndim + 9, "to": 33 * s_ndim}
+
+
 def run_b200(args: argparse.Namespace, emit) -> None:
+    import ctypes
+
     import torch
     import torch.distributed as dist
 
     import ultrasphere_b200 as us
+    from ultrasphere_b200 import _native
     from ultrasphere_b200._host import HostPipeline
 
     rank = int(os.environ.get("RANK", "0"))
@@ -279,11 +389,25 @@ def run_b200(args: argparse.Namespace, emit) -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(values: list[float]) -> list[float]:
+        t = torch.tensor(values, device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(peaks_path):
+        with open(peaks_path) as fh:
+            peak, peak_src = float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    warmup = max(args.warmup, 3)
     sph = None
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warmup):
         sph = c.from_cartesian(x)
         back = c.to_cartesian(sph, as_array=True)
     # parity spot check inside the bench run: the round trip must reproduce the input
@@ -308,21 +432,122 @@ def run_b200(args: argparse.Namespace, emit) -> None:
     sampler.window = (host_t0, time.perf_counter())
     clocks = sampler.stop() if rank == 0 else None
     total_ms = t_begin.elapsed_time(t_end)
-    from_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
-    to_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
-    stats = torch.tensor([total_ms, from_ms, to_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-    total_ms, from_ms, to_ms = (float(v) for v in stats.tolist())
+    from_each = [e[0].elapsed_time(e[1]) for e in ev]
+    to_each = [e[1].elapsed_time(e[2]) for e in ev]
+    from_ms = sum(from_each) / args.steps
+    to_ms = sum(to_each) / args.steps
+    total_ms, from_ms, to_ms = max_over_ranks([total_ms, from_ms, to_ms])
     value = world * n * args.steps / (total_ms * 1e-3)
-    del back, sph
+    del back, sph, x
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configs (C1, C3, C4), same bar: full size per GPU, events, max over ranks ----
+    configs = None
+    if not args.no_configs:
+        configs = {}
+        fma = {}
+        for code, name in ((_native.US_F64, "fp64"), (_native.US_F32, "fp32")):
+            tf = ctypes.c_double()
+            _native.check(_native.lib().us_probe_fma_peak(code, 4096, ctypes.byref(tf)), "us_probe_fma_peak")
+            fma[name] = tf.value
+        fma["fp64"], fma["fp32"] = max_over_ranks([-fma["fp64"], -fma["fp32"]])  # min over ranks
+        fma = {k: -v for k, v in fma.items()}
+        configs["measured_fma_peak_tflops"] = fma
+        leg_steps = max(3, min(args.steps, 10))
+        for key, spec, dname, n_leg, what in LEGS:
+            tdt = torch.float32 if dname == "f32" else torch.float64
+            if key != "C1":
+                n_leg = max(1 << 20, int(n_leg * args.leg_scale))
+            ct = make_tree(us, spec)
+            esz = 4 if dname == "f32" else 8
+            bpp = 2 * ct.c_ndim * esz
+            # inputs larger than L2 (126 MB): C1's 24 MB batch is rotated through enough distinct copies
+            set_bytes = ct.c_ndim * n_leg * esz
+            n_sets = 1 if set_bytes > 2 * L2_BYTES else -(-3 * L2_BYTES // set_bytes)
+            g = torch.Generator(device=dev).manual_seed(4321 + rank)
+            xs = [torch.rand((ct.c_ndim, n_leg), device=dev, dtype=tdt, generator=g).mul_(2).sub_(1) for _ in range(n_sets)]
+            sphs = [ct.from_cartesian(xi) for xi in xs]
+            back = None
+            for i in range(max(3, n_sets)):
+                sphs[i % n_sets] = ct.from_cartesian(xs[i % n_sets])
+                back = ct.to_cartesian(sphs[i % n_sets], as_array=True)
+            eps = 1.1920929e-07 if dname == "f32" else 2.220446049250313e-16
+            j = (max(3, n_sets) - 1) % n_sets
+            m = min(n_leg, 1 << 20)
+            rt_err = ((back[:, :m] - xs[j][:, :m]).abs().amax(0) / sphs[j]["r"][:m]).max().item()
+            if not rt_err <= 16 * eps:
+                configs[key] = {"workload": what, "error": f"round-trip error {rt_err} exceeds 16 eps: not reported"}
+                continue
+            calls = leg_steps * n_sets
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            barrier()
+            e[0].record()
+            for i in range(calls):
+                sphs[i % n_sets] = ct.from_cartesian(xs[i % n_sets])
+            e[1].record()
+            for i in range(calls):
+                back = ct.to_cartesian(sphs[i % n_sets], as_array=True)
+            e[2].record()
+            barrier()
+            f_ms, t_ms = max_over_ranks([e[0].elapsed_time(e[1]) / calls, e[1].elapsed_time(e[2]) / calls])
+            leg = {
+                "workload": what, "dtype": dname, "points_per_gpu": n_leg, "calls_timed": calls,
+                "l2": (f"{n_sets} distinct input sets rotated ({n_sets * set_bytes >> 20} MB > L2)" if n_sets > 1 else "inputs exceed the 126 MB L2"),
+                "from_cartesian_ms": f_ms, "to_cartesian_ms": t_ms,
+                "value": world * n_leg / ((f_ms + t_ms) * 1e-3), "unit": UNIT,
+                "from_points_per_s": world * n_leg / (f_ms * 1e-3), "to_points_per_s": world * n_leg / (t_ms * 1e-3),
+                "round_trip_err_over_r": rt_err,
+                "roofline": {
+                    "bound": "hbm", "unit": "GB/s", "peak": peak, "algorithmic_bytes_per_point": bpp,
+                    "from_cartesian": {"achieved": n_leg * bpp / (f_ms * 1e-3) / 1e9, "frac": n_leg * bpp / (f_ms * 1e-3) / 1e9 / peak},
+                    "to_cartesian": {"achieved": n_leg * bpp / (t_ms * 1e-3) / 1e9, "frac": n_leg * bpp / (t_ms * 1e-3) / 1e9 / peak},
+                },
+            }
+            if dname == "f64":
+                ipp = fp64_instr_per_point(ct.s_ndim, ct.c_ndim)
+                pipe_peak = fma["fp64"] / 2 * 1e12  # FP64-pipe instructions/s: one DFMA = 2 flop
+                leg["fp64_pipe"] = {
+                    "unit": "lane-instructions/s", "peak": pipe_peak, "peak_source": "us_probe_fma_peak (dependent-free DFMA on every SM, this run)",
+                    "from_cartesian": {"instr_per_point": ipp["from"], "frac": ipp["from"] * n_leg / (f_ms * 1e-3) / pipe_peak},
+                    "to_cartesian": {"instr_per_point": ipp["to"], "frac": ipp["to"] * n_leg / (t_ms * 1e-3) / pipe_peak},
+                }
+            if key == "C1":
+                # the same calls without the host's launch cost: 20 calls per CUDA graph, replayed
+                def graph_ms(fn) -> float:
+                    side = torch.cuda.Stream()
+                    side.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(side):
+                        fn(0)
+                    torch.cuda.current_stream().wait_stream(side)
+                    gr = torch.cuda.CUDAGraph()
+                    keep = []
+                    with torch.cuda.graph(gr):
+                        for i in range(20):
+                            keep.append(fn(i))
+                    gr.replay()
+                    torch.cuda.synchronize()
+                    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    g0.record()
+                    for _ in range(5):
+                        gr.replay()
+                    g1.record()
+                    torch.cuda.synchronize()
+                    return g0.elapsed_time(g1) / 100
+
+                gf = graph_ms(lambda i: ct.from_cartesian(xs[i % n_sets]))
+                gt = graph_ms(lambda i: ct.to_cartesian(sphs[i % n_sets], as_array=True))
+                gf, gt = max_over_ranks([gf, gt])
+                leg["eager_note"] = "eager calls: at 1 M points the host's per-call work, not the kernel, sets the time"
+                leg["graph_replay"] = {"from_cartesian_ms": gf, "to_cartesian_ms": gt,
+                                       "from_frac_hbm": n_leg * bpp / (gf * 1e-3) / 1e9 / peak, "to_frac_hbm": n_leg * bpp / (gt * 1e-3) / 1e9 / peak}
+            configs[key] = leg
+            del xs, sphs, back
+            torch.cuda.empty_cache()
 
     # ---- end to end from host buffers (per rank, same tree, E2E_POINTS points) -----------------
     e2e = None
     if not args.no_e2e:
         ne = min(E2E_POINTS, n)
-        del x
-        torch.cuda.empty_cache()
         hx = {k: torch.empty(ne, dtype=torch.float32).uniform_(-1, 1).pin_memory() for k in c.c_nodes}
         hs = {k: torch.empty(ne, dtype=torch.float32).pin_memory() for k in ["r"] + list(c.s_nodes)}
         hb = {k: torch.empty(ne, dtype=torch.float32).pin_memory() for k in c.c_nodes}
@@ -335,11 +560,7 @@ def run_b200(args: argparse.Namespace, emit) -> None:
         for _ in range(esteps):
             pipe.round_trip(hx, hs, hb)
         barrier()
-        dt = time.perf_counter() - t0
-        worst = torch.tensor([dt], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(worst, op=dist.ReduceOp.MAX)
-        dt = float(worst.item())
+        dt = max_over_ranks([time.perf_counter() - t0])[0]
         # variant for information: only the round trip's final result travels back (the spherical
         # coordinates stay in HBM like the intermediate they are in the device-resident number)
         for _ in range(2):
@@ -349,13 +570,43 @@ def run_b200(args: argparse.Namespace, emit) -> None:
         for _ in range(esteps):
             pipe.round_trip(hx, None, hb)
         barrier()
-        dt_final = time.perf_counter() - t0
-        worst = torch.tensor([dt_final], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(worst, op=dist.ReduceOp.MAX)
-        dt_final = float(worst.item())
+        dt_final = max_over_ranks([time.perf_counter() - t0])[0]
         d2h_final = pipe.bytes_d2h
         pipe.round_trip(hx, hs, hb)  # restore the full-result byte counters for the report below
+        # ceiling of the host links for THIS traffic pattern, measured in the same run on every rank
+        # at once: raw pinned copies, H2D and D2H concurrently on two streams, in the ratio the
+        # round trip moves them (40 B/point in, 80 B/point out), nothing else on the GPU
+        link = None
+        try:
+            mb = 1 << 20
+            h_in = torch.empty(160 * mb, dtype=torch.uint8).pin_memory()
+            h_out = torch.empty(320 * mb, dtype=torch.uint8).pin_memory()
+            d_in = torch.empty(160 * mb, dtype=torch.uint8, device=dev)
+            d_out = torch.empty(320 * mb, dtype=torch.uint8, device=dev)
+            s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+            def raw(reps: int) -> None:
+                for _ in range(reps):
+                    with torch.cuda.stream(s_in):
+                        d_in.copy_(h_in, non_blocking=True)
+                    with torch.cuda.stream(s_out):
+                        h_out.copy_(d_out, non_blocking=True)
+                s_in.synchronize()
+                s_out.synchronize()
+
+            raw(2)
+            barrier()
+            t0 = time.perf_counter()
+            raw(6)
+            barrier()
+            ldt = max_over_ranks([time.perf_counter() - t0])[0]
+            h2d_gbs, d2h_gbs = world * 6 * 160 * mb / ldt / 1e9, world * 6 * 320 * mb / ldt / 1e9
+            link = {"h2d_gbs": h2d_gbs, "d2h_gbs": d2h_gbs, "ranks_copying_at_once": world,
+                    "round_trip_ceiling_points_per_s": d2h_gbs * 1e9 / (2 * C_NDIM * 4),
+                    "how": "raw pinned cudaMemcpyAsync, 160 MB host->device and 320 MB device->host concurrently on two streams per rank, 6 repetitions, wall clock, max over ranks"}
+            del h_in, h_out, d_in, d_out
+        except Exception as exc:  # a box that cannot pin another 480 MB: the ceiling is simply not reported
+            link = {"error": f"{type(exc).__name__}: {exc}"}
         bad = max((hb[k][:100000] - hx[k][:100000]).abs().max().item() for k in c.c_nodes)
         if not bad <= 4e-6:
             raise SystemExit(f"bench.py: e2e round-trip error {bad}")
@@ -367,10 +618,15 @@ def run_b200(args: argparse.Namespace, emit) -> None:
             "points_per_step_per_gpu": ne,
             "steps": esteps,
             "launches_per_step": pipe.launches,
+            "host_link_gbs": {"h2d": world * pipe.bytes_h2d * esteps / dt / 1e9, "d2h": world * pipe.bytes_d2h * esteps / dt / 1e9,
+                              "note": "aggregate over all ranks during the timed steps: the box's host links bound this number, not the kernels"},
+            "host_link_ceiling": link,
+            "frac_of_link_ceiling": (world * ne * esteps / dt) / link["round_trip_ceiling_points_per_s"] if link and "round_trip_ceiling_points_per_s" in link else None,
             "final_result_only": {"value": world * ne * esteps / dt_final, "unit": UNIT, "d2h_bytes_per_step": d2h_final,
                                   "note": "same pipeline, only the reconstructed Cartesian points are copied back"},
             "how": "pinned host dict-of-arrays -> HostPipeline.round_trip (chunked H2D / from_cartesian / to_cartesian / D2H of spherical and Cartesian results on 3 streams), wall clock around the calls, max over ranks",
         }
+        del hx, hs, hb, pipe
 
     # ---- quadrature leg: the second half of the metric (BASELINE.json configs[4]) ----------------
     # us.integrate on create_standard(4), n = 96 (169,869,312 nodes), float64, f = exp(k.x); the
@@ -378,11 +634,8 @@ def run_b200(args: argparse.Namespace, emit) -> None:
     # scalar.  Two integrands: the reference's own form (materialises the Cartesian grid, then
     # torch.einsum) and the fused functional.  CUDA events, max over ranks.
     quadrature = None
+    multi_rank_check = None
     if not args.no_quadrature:
-        try:
-            del x
-        except NameError:
-            pass
         torch.cuda.empty_cache()
         import numpy as np
 
@@ -415,14 +668,30 @@ def run_b200(args: argparse.Namespace, emit) -> None:
                 got = run()
             q1.record()
             barrier()
-            ms = torch.tensor([q0.elapsed_time(q1) / reps], device=dev, dtype=torch.float64)
-            if world > 1:
-                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            ms = max_over_ranks([q0.elapsed_time(q1) / reps])[0]
             rel = abs(got.item() - want) / want
             if not rel <= 1e-12:  # the same all-reduced value on every rank: no number for this leg, the line still prints
                 quadrature[name] = {"error": f"integral off by {rel} relative: not reported", "rel_err_vs_analytic": rel}
                 continue
-            quadrature[name] = {"ms_per_integral": float(ms.item()), "nodes_per_s": nodes / (float(ms.item()) * 1e-3), "rel_err_vs_analytic": rel}
+            quadrature[name] = {"ms_per_integral": ms, "nodes_per_s": nodes / (ms * 1e-3), "rel_err_vs_analytic": rel}
+        if world > 1:
+            # the check of tests/test_gpu_multi.py under THIS run's ranks: every sharded integral
+            # (two trees, both integrand forms, slabbed) against the same integral unsharded
+            worst = 0.0
+            cases = 0
+            for ct, nn_ in ((us.create_standard(4), 24), (us.create_hopf(2), 17)):
+                kk = torch.from_numpy(np.random.default_rng(0).uniform(0, 1, ct.c_ndim)).to(dev)
+                plain = lambda s_, ct=ct, kk=kk: torch.exp(torch.einsum("v,v...->...", kk, ct.to_cartesian(s_, as_array=True)))  # noqa: E731
+                fused = lambda s_, ct=ct, kk=kk: torch.exp(ct.to_cartesian_dot(s_, kk))  # noqa: E731
+                kw = dict(xp=torch, device=dev, dtype=torch.float64)
+                single = us.integrate(ct, plain, False, nn_, **kw).item()
+                for fn, extra in ((plain, {}), (fused, {"slab_bytes": 1 << 16})):
+                    got = us.integrate(ct, fn, False, nn_, group=group, **extra, **kw).item()
+                    worst = max(worst, abs(got - single) / abs(single))
+                    cases += 1
+            worst = max_over_ranks([worst])[0]
+            multi_rank_check = {"ranks": world, "cases": cases, "max_rel_diff_sharded_vs_unsharded": worst, "ok": bool(worst <= 1e-12),
+                                "what": "integrate(group=WORLD) on create_standard(4) n=24 and create_hopf(2) n=17, both integrand forms, against group=None on the same GPU"}
         torch.cuda.empty_cache()
 
     if rank != 0:
@@ -430,17 +699,11 @@ def run_b200(args: argparse.Namespace, emit) -> None:
             dist.destroy_process_group()
         return
 
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.isfile(peaks_path):
-        with open(peaks_path) as fh:
-            peak, peak_src = float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     dom, dom_ms = ("us::from_cartesian", from_ms) if from_ms >= to_ms else ("us::to_cartesian", to_ms)
     alg_bytes = BYTES_PER_POINT_ONE_WAY * n
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
     # DRAM traffic of the dominant kernel: dram__bytes_read+write from the committed `ncu --set full`
-    # capture (profiles/traffic_rNN.json, taken at a smaller batch), scaled to this launch's size
+    # capture (profiles/traffic_rNN.json), scaled to this launch's size if the capture's differs
     traffic, traffic_src = None, None
     tfiles = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.startswith("traffic_r") and f.endswith(".json")) if os.path.isdir(os.path.join(ROOT, "profiles")) else []
     if tfiles:
@@ -448,16 +711,18 @@ def run_b200(args: argparse.Namespace, emit) -> None:
             rec = json.load(fh).get(dom)
         if rec:
             traffic = rec["ratio"] * alg_bytes
-            traffic_src = f"profiles/{tfiles[-1]}: measured/algorithmic = {rec['ratio']:.4f} at 64 M points, scaled to this launch"
+            traffic_src = f"profiles/{tfiles[-1]}: measured/algorithmic = {rec['ratio']:.4f} at {rec.get('points', 64_000_000) / 1e6:.0f} M points, scaled to this launch"
     roofline = {
         "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
         "ms_per_launch": dom_ms,
         "other_kernel": {"from_cartesian_ms": from_ms, "to_cartesian_ms": to_ms,
-                         "from_cartesian_gbs": alg_bytes / (from_ms * 1e-3) / 1e9, "to_cartesian_gbs": alg_bytes / (to_ms * 1e-3) / 1e9},
+                         "from_cartesian_gbs": alg_bytes / (from_ms * 1e-3) / 1e9, "to_cartesian_gbs": alg_bytes / (to_ms * 1e-3) / 1e9,
+                         "from_cartesian_frac": alg_bytes / (from_ms * 1e-3) / 1e9 / peak, "to_cartesian_frac": alg_bytes / (to_ms * 1e-3) / 1e9 / peak},
+        "per_step_ms_rank0": {"from_cartesian": [round(v, 4) for v in from_each], "to_cartesian": [round(v, 4) for v in to_each]},
     }
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {
@@ -467,10 +732,13 @@ def run_b200(args: argparse.Namespace, emit) -> None:
             "inputs": "U(-1,1) per leaf, torch.Generator(cuda).manual_seed(1234+rank), resident in HBM",
         },
         "roofline": roofline, "e2e": e2e, "gpu_launches": 2 * args.steps, "clocks": clocks,
-        "quadrature": quadrature,
+        "configs": configs, "quadrature": quadrature, "multi_rank_check": multi_rank_check,
     }
-    if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline_single_core(min(CPU_SAMPLE, n))
+    if not args.no_cpu_baseline:
+        if world == 1:
+            line["cpu_baseline"] = cpu_baseline_single_core(min(CPU_SAMPLE, n))
+        else:
+            line["cpu_baseline"] = {"value": None, "note": "timed on rank 0 at N=1 only (the contract): see the --gpus 1 line of the same scaling run"}
     emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

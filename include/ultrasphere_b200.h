@@ -84,7 +84,7 @@ typedef struct us_plan {
   int32_t n_nodes;   /* s_ndim */
   int32_t n_leaves;  /* c_ndim = n_nodes + 1 */
   int32_t max_stack; /* deepest deferred-branch stack the program needs */
-  int32_t reserved;
+  int32_t reserved;  /* seal written by us_plan_compile; every entry point refuses a plan whose seal does not match */
   uint64_t node[US_MAX_NODES];
 } us_plan_t;
 
@@ -152,6 +152,19 @@ US_API int us_to_cartesian_ws(const us_plan_t* plan, int dtype, int64_t n, int n
 US_API int us_from_cartesian(const us_plan_t* plan, int dtype, int64_t n, int ndim, const int64_t* shape,
                       const void* const* x_dev, const uint32_t* x_mask, void* r_out_dev,
                       void* const* angle_out_dev, void* stream);
+
+/*
+ * Row-matrix forms of the two transforms for the common dense case: the leaves are the rows of one
+ * C-contiguous (c_ndim, n) matrix x_dev (row pitch x_row_bytes), the results the rows of out_dev —
+ * from: row 0 = r, row 1 + s = angle s (s_nodes order); to: row l = leaf l (c_nodes order).  Same
+ * kernels and results as us_from_cartesian / us_to_cartesian; a binding calls these to avoid
+ * building pointer and mask tables per call (what SphericalCoordinates.from_cartesian(array) and
+ * to_cartesian(..., as_array=True) need, _coordinates.py:555-563, 650-654).
+ */
+US_API int us_from_cartesian_rows(const us_plan_t* plan, int dtype, int64_t n, const void* x_dev, int64_t x_row_bytes,
+                                  void* out_dev, int64_t out_row_bytes, void* stream);
+US_API int us_to_cartesian_rows(const us_plan_t* plan, int dtype, int64_t n, const void* const* angle_dev,
+                                const void* r_dev, void* out_dev, int64_t out_row_bytes, void* stream);
 
 /*
  * out[m] (+)= sum over the grid of  prod_i w_i[idx_i] * val[idx_0, ..., idx_{ndim-1}, m]

@@ -196,8 +196,14 @@ def roots(
     dtype: Any | None = None,
     xp: Any,
 ) -> tuple[dict[Any, torch.Tensor], dict[Any, torch.Tensor]]:
-    """Quadrature angles and weights per node of ``c.s_nodes`` (1-D, or broadcastable N-D)."""
+    """Quadrature angles and weights per node of ``c.s_nodes`` (1-D, or broadcastable N-D).
+
+    Every call returns fresh tensors (like the reference, _integral.py:108-109): the cached host
+    tables are copied, never aliased.  ``device=None`` means the current CUDA device; on a machine
+    without one (the tables alone need no kernel) it means the host, as in the reference."""
     _check_xp(xp)
+    if device is None and torch.cuda.is_available():
+        device = torch.device("cuda", torch.cuda.current_device())
     xs: dict[Any, torch.Tensor] = {}
     ws: dict[Any, torch.Tensor] = {}
     on_device = _rules_on_device(c, n, device, dtype) if _rule_backend == "device" else None
@@ -208,8 +214,8 @@ def roots(
             x = torch.arange(2 * n, device=device, dtype=dtype) * torch.pi / n
             w = torch.ones(2 * n, device=device, dtype=dtype) * torch.pi / n
         else:
-            x = torch.asarray(rule[0], device=device, dtype=dtype)
-            w = torch.asarray(rule[1], device=device, dtype=dtype)
+            x = torch.tensor(rule[0], device=device, dtype=dtype)  # a copy: the cache stays private
+            w = torch.tensor(rule[1], device=device, dtype=dtype)
         index = (None,) * i + (slice(None),) + (None,) * (c.s_ndim - i - 1)
         xs[node] = x[index] if expand_dims_x else x
         ws[node] = w[index] if expand_dims_w else w
@@ -299,7 +305,20 @@ def weighted_reduce(
 def _weighted_reduce(val: torch.Tensor, weights: list[torch.Tensor], *, out: torch.Tensor | None) -> torch.Tensor:
     k = len(weights)
     device = val.device
-    val = _as_supported(val, weights[0].dtype)
+    if k > _native.US_MAX_DIMS:
+        # more grid axes than one launch indexes: contract the leading US_MAX_DIMS axes (the rest
+        # rides along as trailing elements), then the remainder the same way
+        head = _native.US_MAX_DIMS
+        part = _weighted_reduce(val, weights[:head], out=None)
+        res = _weighted_reduce(part, weights[head:], out=None)
+        if out is None:
+            return res
+        out += res
+        return out
+    wdtype = weights[0].dtype
+    for w in weights[1:]:
+        wdtype = torch.promote_types(wdtype, w.dtype)
+    val = _as_supported(val, wdtype)
     rv, is_complex = _real_view(val)
     if not rv.is_contiguous():
         rv = rv.contiguous()
@@ -360,8 +379,10 @@ def separable_reduce(vals: list[torch.Tensor], weights: list[torch.Tensor]) -> l
     prepared = []
     outs: list[torch.Tensor] = []
     real_dtype = None
+    own_dtypes = []
     for v, w in zip(vals, weights):
         v = _as_supported(v, w.dtype)
+        own_dtypes.append(v.dtype)  # what the reference's vecdot(w_a, val_a) returns for this axis
         rv, is_complex = _real_view(v)
         rv = rv if rv.is_contiguous() else rv.contiguous()
         prepared.append((rv, is_complex, tuple(v.shape[1:])))
@@ -403,7 +424,8 @@ def separable_reduce(vals: list[torch.Tensor], weights: list[torch.Tensor]) -> l
                 _stream_ptr(device),
             )
         _native.check(status, "us_separable_reduce")
-    return outs
+    # the launch computes every axis in the widest type present; each result goes back to its own
+    return [o if o.dtype == dt else o.to(dt) for o, dt in zip(outs, own_dtypes)]
 
 
 # --------------------------------------------------------------------------------------
@@ -439,8 +461,9 @@ def _device_rules(
 
 
 def _sum_weight(w: torch.Tensor) -> torch.Tensor:
-    """1-element weight table for an axis the integrand is constant along (sum of the rule)."""
-    return w.sum(dtype=torch.float64).reshape(1)
+    """1-element weight table for an axis the integrand is constant along (sum of the rule, summed
+    in float64, kept in the rule's dtype so that the result dtype follows the reference's promotion)."""
+    return w.sum(dtype=torch.float64).to(w.dtype).reshape(1)
 
 
 def _contract_dense(

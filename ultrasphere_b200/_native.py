@@ -74,6 +74,8 @@ _SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
         C.c_int,
         [C.POINTER(UsPlan), C.c_int, C.c_int64, C.c_int, _PI64, _PP, _PU32, C.c_void_p, _PP, C.c_void_p],
     ),
+    "us_from_cartesian_rows": (C.c_int, [C.POINTER(UsPlan), C.c_int, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
+    "us_to_cartesian_rows": (C.c_int, [C.POINTER(UsPlan), C.c_int, C.c_int64, _PP, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "us_weighted_reduce_scratch_bytes": (C.c_int64, [C.c_int64]),
     "us_weighted_reduce": (
         C.c_int,

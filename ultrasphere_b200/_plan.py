@@ -22,7 +22,9 @@ _KIND = {BranchingType.A: 0, BranchingType.B: 1, BranchingType.BP: 2, BranchingT
 
 @dataclass(frozen=True)
 class CompiledTree:
-    """Host-side view of a compiled tree (everything index-based, no graph objects)."""
+    """Host-side view of a compiled tree (everything index-based, no graph objects), plus what the
+    dense fast paths of ``_transform`` would otherwise rebuild on every call: the plan reference,
+    the bound entry points, a reusable pointer table and the output dict order."""
 
     plan: _native.UsPlan
     n_nodes: int
@@ -38,6 +40,12 @@ class CompiledTree:
     leaf_ancestors: tuple[tuple[int, ...], ...]
     # per s_nodes index: indices (into c_nodes) of the leaves below the node
     angle_leaves: tuple[tuple[int, ...], ...]
+    plan_ref: Any = None        # ctypes.byref(plan)
+    from_rows: Any = None       # lib.us_from_cartesian_rows
+    to_rows: Any = None         # lib.us_to_cartesian_rows
+    angle_ptrs: Any = None      # (c_void_p * n_nodes)()
+    ones_leaves: Any = None     # (c_uint32 * n_leaves)(1, ...): "spans the launch" masks
+    from_order: tuple[tuple[Any, int], ...] = ()  # (node, row of from_cartesian's output) in dict order
 
 
 def preorder_listing(c: SphericalCoordinates[Any, Any]) -> tuple[list[Any], list[int], list[Any]]:
@@ -121,6 +129,12 @@ def compile_tree(c: SphericalCoordinates[Any, Any]) -> CompiledTree:
         angle_ancestors=angle_anc,
         leaf_ancestors=leaf_anc,
         angle_leaves=tuple(tuple(b) for b in below),
+        plan_ref=C.byref(plan),
+        from_rows=_native.lib().us_from_cartesian_rows,
+        to_rows=_native.lib().us_to_cartesian_rows,
+        angle_ptrs=(C.c_void_p * n)(),
+        ones_leaves=(C.c_uint32 * (n + 1))(*([1] * (n + 1))),
+        from_order=tuple((c.s_nodes[s], 1 + s) for s in range(n - 1, -1, -1)),
     )
 
 

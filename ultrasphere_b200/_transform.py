@@ -399,9 +399,10 @@ def _to_cartesian_dense(
 ) -> Any:
     """The common case with the least host work: every operand a dense CUDA tensor of one shape
     and one float dtype (r absent, 1, or such a tensor too).  Returns None if the case is not this
-    one; the general path then validates, promotes and broadcasts."""
+    one; the general path then validates, promotes and broadcasts.  One ``torch.empty``, one call
+    of ``us_to_cartesian_rows`` (outputs = rows of the allocation: no pointer or mask tables)."""
     first = angles[0]
-    if not isinstance(first, torch.Tensor) or not first.is_cuda:
+    if type(first) is not torch.Tensor or not first.is_cuda:
         return None
     dtype, shape, device = first.dtype, first.shape, first.device
     code = _DTYPE_CODE.get(dtype)
@@ -413,37 +414,35 @@ def _to_cartesian_dense(
         ops = angles
     else:
         return None
+    grad = torch.is_grad_enabled()
     for t in ops:
         if (
-            not isinstance(t, torch.Tensor)
+            type(t) is not torch.Tensor
             or t.dtype != dtype
             or t.shape != shape
             or t.device != device
             or not t.is_contiguous()
-            or (t.requires_grad and torch.is_grad_enabled())
+            or (grad and t.requires_grad)
         ):
             return None
-    ct = plan_for(c)
+    ct = c._plan or plan_for(c)
     n = first.numel()
     out = torch.empty((ct.n_leaves, *shape), dtype=dtype, device=device)
     if n:
-        row_bytes = n * out.element_size()
-        base = out.data_ptr()
-        with device_guard(device):
-            status = _native.lib().us_to_cartesian(
-                C.byref(ct.plan),
-                code,
-                n,
-                1,
-                _native.i64_array([n]),
-                _native.void_p_array([a.data_ptr() for a in angles]),
-                _native.u32_array([1] * ct.n_nodes),
-                r.data_ptr() if r_is_tensor else None,
-                1,
-                _native.void_p_array([base + i * row_bytes for i in range(ct.n_leaves)]),
-                _stream_ptr(device),
+        ptrs = ct.angle_ptrs  # reused table: filled and consumed under the GIL, before the call returns
+        for i, a in enumerate(angles):
+            ptrs[i] = a.data_ptr()
+        if device.index != torch.cuda.current_device():
+            with torch.cuda.device(device):
+                status = _native.lib().us_to_cartesian_rows(
+                    ct.plan_ref, code, n, ptrs, r.data_ptr() if r_is_tensor else None, out.data_ptr(), n * out.element_size(), _raw_stream(device.index)
+                )
+        else:
+            status = ct.to_rows(
+                ct.plan_ref, code, n, ptrs, r.data_ptr() if r_is_tensor else None, out.data_ptr(), n * out.element_size(), _raw_stream(device.index)
             )
-        _native.check(status, "us_to_cartesian")
+        if status:
+            _native.check(status, "us_to_cartesian")
     if as_array:
         return out
     return dict(zip(c.c_nodes, out.unbind(0)))
@@ -589,72 +588,83 @@ def to_cartesian_dot(c: SphericalCoordinates[Any, Any], spherical: Mapping[Any, 
 # from_cartesian
 # --------------------------------------------------------------------------------------
 def _from_cartesian_dense(c: SphericalCoordinates[Any, Any], cartesian: Any) -> dict[Any, Any] | None:
-    """Least host work for the two common inputs: one dense ``(c_ndim, *shape)`` CUDA tensor, or a
-    mapping of dense equal-shape CUDA tensors.  None if the input is anything else."""
+    """Least host work for the two common inputs: one dense ``(c_ndim, *shape)`` CUDA tensor (one
+    call of ``us_from_cartesian_rows``: base pointers and row pitches, no tables), or a mapping of
+    dense equal-shape CUDA tensors.  None if the input is anything else."""
     ct_nodes = c.c_nodes
-    if isinstance(cartesian, torch.Tensor):
+    grad = torch.is_grad_enabled()
+    ct = c._plan or plan_for(c)
+    if type(cartesian) is torch.Tensor:
         x = cartesian
         if (
             not x.is_cuda
             or x.dim() < 1
-            or x.shape[0] != len(ct_nodes)
+            or x.shape[0] != ct.n_leaves
             or not x.is_contiguous()
             or not c.is_c_keys_sorted_range
-            or (x.requires_grad and torch.is_grad_enabled())
+            or (grad and x.requires_grad)
         ):
             return None
-        dtype, shape, device = x.dtype, x.shape[1:], x.device
-        n = x.numel() // len(ct_nodes)
-        row = n * x.element_size()
-        in_ptrs = [x.data_ptr() + i * row for i in range(len(ct_nodes))]
+        dtype, device = x.dtype, x.device
+        code = _DTYPE_CODE.get(dtype)
+        if code is None:
+            return None
+        n = x.numel() // ct.n_leaves
+        out = torch.empty((ct.n_nodes + 1, *x.shape[1:]), dtype=dtype, device=device)
+        if n:
+            row = n * x.element_size()
+            if device.index != torch.cuda.current_device():
+                with torch.cuda.device(device):
+                    status = ct.from_rows(ct.plan_ref, code, n, x.data_ptr(), row, out.data_ptr(), row, _raw_stream(device.index))
+            else:
+                status = ct.from_rows(ct.plan_ref, code, n, x.data_ptr(), row, out.data_ptr(), row, _raw_stream(device.index))
+            if status:
+                _native.check(status, "us_from_cartesian")
     else:
         try:
             leaves = [cartesian[k] for k in ct_nodes]
         except (KeyError, IndexError, TypeError):
             return None
         first = leaves[0]
-        if not isinstance(first, torch.Tensor) or not first.is_cuda:
+        if type(first) is not torch.Tensor or not first.is_cuda:
             return None
         dtype, shape, device = first.dtype, first.shape, first.device
         for t in leaves:
             if (
-                not isinstance(t, torch.Tensor)
+                type(t) is not torch.Tensor
                 or t.dtype != dtype
                 or t.shape != shape
                 or t.device != device
                 or not t.is_contiguous()
-                or (t.requires_grad and torch.is_grad_enabled())
+                or (grad and t.requires_grad)
             ):
                 return None
+        code = _DTYPE_CODE.get(dtype)
+        if code is None:
+            return None
         n = first.numel()
-        in_ptrs = [t.data_ptr() for t in leaves]
-    code = _DTYPE_CODE.get(dtype)
-    if code is None:
-        return None
-    ct = plan_for(c)
-    out = torch.empty((ct.n_nodes + 1, *shape), dtype=dtype, device=device)
-    if n:
-        row_bytes = n * out.element_size()
-        base = out.data_ptr()
-        with device_guard(device):
-            status = _native.lib().us_from_cartesian(
-                C.byref(ct.plan),
-                code,
-                n,
-                1,
-                _native.i64_array([n]),
-                _native.void_p_array(in_ptrs),
-                _native.u32_array([1] * ct.n_leaves),
-                base,
-                _native.void_p_array([base + (1 + s) * row_bytes for s in range(ct.n_nodes)]),
-                _stream_ptr(device),
-            )
-        _native.check(status, "us_from_cartesian")
+        out = torch.empty((ct.n_nodes + 1, *shape), dtype=dtype, device=device)
+        if n:
+            row_bytes = n * out.element_size()
+            base = out.data_ptr()
+            with device_guard(device):
+                status = _native.lib().us_from_cartesian(
+                    ct.plan_ref,
+                    code,
+                    n,
+                    1,
+                    _native.i64_array([n]),
+                    _native.void_p_array([t.data_ptr() for t in leaves]),
+                    ct.ones_leaves,
+                    base,
+                    _native.void_p_array([base + (1 + s) * row_bytes for s in range(ct.n_nodes)]),
+                    _stream_ptr(device),
+                )
+            _native.check(status, "us_from_cartesian")
     rows = out.unbind(0)
     result: dict[Any, Any] = {"r": rows[0]}
-    s_nodes = c.s_nodes
-    for s in range(ct.n_nodes - 1, -1, -1):  # dict order: "r", then children before parents
-        result[s_nodes[s]] = rows[1 + s]
+    for node, s in ct.from_order:  # dict order: "r", then children before parents
+        result[node] = rows[s]
     return result
 
 

@@ -24,12 +24,33 @@ int cuda_fail(cudaError_t e, const char* where) {
   return (int)e;
 }
 
-static int check_plan(const us_plan_t* plan, const char* who) {
+// us_plan_t is a plain public struct and the kernels index their pointer tables with the fields of
+// its node words without range checks, so a plan is only accepted with the seal us_plan_compile put
+// on it (FNV-1a over the counts and the words; never 0): a hand-built or corrupted plan is refused
+// with US_EPLAN instead of reading or writing out of bounds on the device.
+static int32_t plan_seal(const us_plan_t* plan) {
+  uint64_t h = 1469598103934665603ull;
+  auto mix = [&h](uint64_t v) {
+    for (int b = 0; b < 8; ++b) {
+      h ^= (v >> (8 * b)) & 0xFFu;
+      h *= 1099511628211ull;
+    }
+  };
+  mix((uint64_t)(uint32_t)plan->n_nodes | ((uint64_t)(uint32_t)plan->n_leaves << 32));
+  mix((uint64_t)(uint32_t)plan->max_stack);
+  for (int i = 0; i < plan->n_nodes; ++i) mix(plan->node[i]);
+  const int32_t s = (int32_t)(h ^ (h >> 32));
+  return s ? s : 1;
+}
+
+int check_plan(const us_plan_t* plan, const char* who) {
   if (!plan) return fail(US_EINVAL, "%s: null plan", who);
   if (plan->n_nodes < 1 || plan->n_nodes > US_MAX_NODES || plan->n_leaves != plan->n_nodes + 1)
     return fail(US_EPLAN, "%s: plan has %d nodes / %d leaves", who, plan->n_nodes, plan->n_leaves);
   if (plan->max_stack < 0 || plan->max_stack > US_MAX_STACK)
     return fail(US_ECAPACITY, "%s: plan needs a stack of %d > %d", who, plan->max_stack, US_MAX_STACK);
+  if (plan->reserved != plan_seal(plan))
+    return fail(US_EPLAN, "%s: plan was not produced by us_plan_compile (or was modified afterwards)", who);
   return 0;
 }
 
@@ -119,6 +140,7 @@ extern "C" int us_plan_compile(int32_t n_nodes, const uint8_t* kinds, const int3
   out->n_nodes = n_nodes;
   out->n_leaves = n_leaves;
   out->max_stack = max_sp;
+  out->reserved = plan_seal(out);
   return 0;
 }
 
@@ -234,6 +256,38 @@ extern "C" int us_from_cartesian(const us_plan_t* plan, int dtype, int64_t n, in
   const int rc = try_launch_from_cartesian_tiled(p, dtype, st);
   if (rc != kNotTaken) return rc;
   return launch_from_cartesian_strided(p, dtype, st);
+}
+
+// ---- row-matrix forms: the common dense case with the least work on the caller's side -----------
+// Every operand is a row of one C-contiguous (rows, n) matrix, so the caller passes a base pointer
+// and a row pitch instead of building pointer and mask tables (a binding's per-call cost is what
+// bounds small batches: a 10^6-point float64 create_spherical() launch takes ~7 us).
+extern "C" int us_from_cartesian_rows(const us_plan_t* plan, int dtype, int64_t n, const void* x_dev, int64_t x_row_bytes,
+                                      void* out_dev, int64_t out_row_bytes, void* stream) {
+  static const char* who = "us_from_cartesian_rows";
+  if (int rc = check_plan(plan, who)) return rc;
+  if (n > 0 && (!x_dev || !out_dev)) return fail(US_EINVAL, "%s: null matrix", who);
+  const void* x[US_MAX_LEAVES];
+  uint32_t mask[US_MAX_LEAVES];
+  void* out[US_MAX_NODES];
+  for (int l = 0; l < plan->n_leaves; ++l) {
+    x[l] = (const char*)x_dev + (int64_t)l * x_row_bytes;
+    mask[l] = 1u;
+  }
+  for (int s = 0; s < plan->n_nodes; ++s) out[s] = (char*)out_dev + (int64_t)(1 + s) * out_row_bytes;
+  return us_from_cartesian(plan, dtype, n, 1, &n, x, mask, out_dev, out, stream);
+}
+
+extern "C" int us_to_cartesian_rows(const us_plan_t* plan, int dtype, int64_t n, const void* const* angle_dev,
+                                    const void* r_dev, void* out_dev, int64_t out_row_bytes, void* stream) {
+  static const char* who = "us_to_cartesian_rows";
+  if (int rc = check_plan(plan, who)) return rc;
+  if (!angle_dev || (n > 0 && !out_dev)) return fail(US_EINVAL, "%s: null pointer", who);
+  uint32_t mask[US_MAX_NODES];
+  void* out[US_MAX_LEAVES];
+  for (int s = 0; s < plan->n_nodes; ++s) mask[s] = 1u;
+  for (int l = 0; l < plan->n_leaves; ++l) out[l] = (char*)out_dev + (int64_t)l * out_row_bytes;
+  return us_to_cartesian_ws(plan, dtype, n, 1, &n, angle_dev, mask, r_dev, 1u, out, nullptr, 0, stream);
 }
 
 // ---- FMA peak probe ----------------------------------------------------------------------

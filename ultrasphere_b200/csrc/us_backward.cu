@@ -182,10 +182,7 @@ __global__ void __launch_bounds__(256) from_cartesian_backward(const __grid_cons
 }
 
 static int check_backward(const us_plan_t* plan, int dtype, int64_t n, const char* who) {
-  if (!plan) return fail(US_EINVAL, "%s: null plan", who);
-  if (plan->n_nodes < 1 || plan->n_nodes > US_MAX_NODES || plan->n_leaves != plan->n_nodes + 1)
-    return fail(US_EPLAN, "%s: plan has %d nodes / %d leaves", who, plan->n_nodes, plan->n_leaves);
-  if (plan->max_stack < 0 || plan->max_stack > US_MAX_STACK) return fail(US_ECAPACITY, "%s: plan needs a stack of %d", who, plan->max_stack);
+  if (int rc = check_plan(plan, who)) return rc;
   if (dtype != US_F32 && dtype != US_F64) return fail(US_EINVAL, "%s: bad dtype %d", who, dtype);
   if (n < 0) return fail(US_EINVAL, "%s: n < 0", who);
   if ((n + 255) / 256 > 0x7FFFFFFFLL) return fail(US_EINVAL, "%s: n too large for one launch", who);

@@ -25,6 +25,9 @@ struct XformParams {
 };
 static_assert(sizeof(XformParams) < 32000, "kernel parameter block must fit the 32 KB limit");
 
+// counts, capacities and the seal of us_plan_compile (us_api.cu)
+int check_plan(const us_plan_t* plan, const char* who);
+
 int launch_to_cartesian_strided(const XformParams& p, int dtype, cudaStream_t st);
 int launch_from_cartesian_strided(const XformParams& p, int dtype, cudaStream_t st);
 int launch_jacobian_strided(const XformParams& p, const int32_t* cos_pow, const int32_t* sin_pow, int dtype, cudaStream_t st);
@@ -45,5 +48,6 @@ template <bool TO>
 int launch_ring(const XformParams& p, int dtype, cudaStream_t st, int* points_per_tile);
 // cached cudaFuncSetAttribute(max dynamic smem) + occupancy query
 int resident_ctas(const void* fn, size_t smem, int block_threads, int* per_sm);
+int sm_count();  // of the current device, cached
 
 }  // namespace us

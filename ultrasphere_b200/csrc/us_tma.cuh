@@ -31,27 +31,59 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Wait for a phase, called by ALL lanes of a converged warp.  The loop condition is a warp vote, so
+// the warp leaves the loop as one: with barrier address and parity in uniform registers ptxas
+// treats the predicate of a plain `while (!try_wait)` as warp-uniform, keeps the surrounding loop
+// state (tile cursor, buffer index, parity) in uniform registers and drops the __syncwarp() before
+// the release — but the hardware may answer the lanes of one try_wait differently when the phase
+// completes while the instruction is in flight, and a warp that splits there runs the tile twice
+// on shared uniform registers (seen as hangs and launch failures at 6 * 10^7 points and more).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {
+  while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
   }
 }
 // The same on shared-space (32-bit) addresses computed once per kernel: the generic-pointer forms
 // above rebuild the shared window base (S2R CgaCtaId + LEA + ...) at every call site, which the
 // row-ring kernels pay per row and per thread.
-__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait_s(uint32_t bar, uint32_t parity) {
   uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!ok);
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
+  while (!__all_sync(0xffffffffu, mbar_try_wait_s(bar, parity))) {
+  }
+}
+// Wait by ONE thread (the elected lane of a producer warp, a single-thread role): no vote.
+__device__ __forceinline__ void mbar_wait_one(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
 }
 __device__ __forceinline__ void mbar_arrive_s(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Warp index and leader election in the forms ptxas recognises as warp-uniform: the producer loops
+// then keep their tile counters, buffer indices and addresses in uniform registers and issue each
+// bulk copy with three or four instructions.  (With a lane picked by `threadIdx.x & 31` the same
+// loop ran in vector registers: every UBLKCP was wrapped in R2UR moves and an ELECT retry loop,
+// ~17 instructions of a serial chain per row, and ncu showed the consumer warps waiting 10-23 % of
+// their time for tiles one starved producer thread had not issued yet.)
+__device__ __forceinline__ int warp_index_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 // global -> shared bulk copy through the TMA unit; bytes % 16 == 0, both addresses 16-byte aligned

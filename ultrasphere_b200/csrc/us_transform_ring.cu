@@ -1,111 +1,144 @@
 // Cartesian <-> polyspherical transforms: contiguous fast path for WIDE trees.
 //
-// The tile kernels (us_transform_tiled.cu) keep every input row of a tile resident, two stages
-// deep: 2 * rows * 16 B of shared memory per consumer thread.  Beyond ~13 rows that no longer
-// leaves room for 16-byte vectors and two CTAs per SM (create_random(32) has 33 rows).  Here the
-// rows stream through a RING of kRing row slots instead: the producer warp issues one TMA bulk
-// copy per (tile, row) in exactly the order the consumers will need them, each slot has its own
-// full/empty mbarrier pair, and a consumer warp releases a slot as soon as it has used the row.
-// Shared memory per CTA is kRing * 4 KB whatever the tree width, threads keep V = 16 B / sizeof(T).
+// The tile kernels (us_transform_tiled.cu) keep every input row of a tile resident.  Beyond ~13
+// rows a pool of whole tiles no longer leaves room for enough consumer warps (create_random(32)
+// has 33 rows).  Here the rows stream through a RING of row slots instead: the producer warp
+// issues one TMA bulk copy per (tile, row) in exactly the order the consumers will need them, each
+// slot has its own full/empty mbarrier pair, and a consumer warp releases a slot as soon as it has
+// used the row.  Shared memory per CTA is (slots + parking rows) * 4 KB whatever the tree width,
+// threads keep V = 16 B / sizeof(T).  Deferred branches of `c` nodes are parked in shared memory
+// rows indexed by the depth of the deferral (us_walk.cuh): no per-thread stack, no local memory.
 //
 //   to_cartesian    row order per tile: r (if given), then the angle of every node in program order
 //   from_cartesian  two passes over a tile's leaves: c_nodes order for r (sequential sum, bit-exact),
 //                   then the leaf operands of the nodes in reverse program order.  The second pass
 //                   re-reads rows the first one just fetched: they are loaded with an L2 evict-last
 //                   hint the first time and evict-first the second, so DRAM still sees each byte once.
+#include <mutex>
+
 #include "us_common.cuh"
 #include "us_params.cuh"
 #include "us_tma.cuh"
+#include "us_walk.cuh"
 
 namespace us {
 
-constexpr int kRing = 16;            // row slots (power of two)
+constexpr int kMaxRing = 16;         // row slots at most
 constexpr int kRingConsumers = 256;  // consumer threads = points per tile / V
 constexpr int kRingBlock = kRingConsumers + 32;
+constexpr int kRingRowBytes = kRingConsumers * 16;
+
+using RingParams = WalkParams<US_MAX_NODES>;
 
 struct RingShared {
-  uint64_t full[kRing];
-  uint64_t empty[kRing];
+  uint64_t full[kMaxRing];
+  uint64_t empty[kMaxRing];
 };
+constexpr int kRingHeader = 256;
+static_assert(sizeof(RingShared) <= kRingHeader, "barrier block");
 
 // Consumer side, on shared-space addresses computed once per thread: `mine` already points at this
-// thread's 16 bytes of slot 0, slots are P*sizeof(T) apart, barriers 8 bytes apart.
+// thread's 16 bytes of slot 0, slots are 4 KB apart, barriers 8 bytes apart.
 template <typename T, int V>
 struct RingConsumer {
   uint32_t mine, full, empty;
-  uint32_t q;
+  uint32_t slot, parity, n_slots;
   bool lane0;
-  static constexpr int P = kRingConsumers * V;
-  __device__ __forceinline__ RingConsumer(const T* rows, RingShared* sh, int tid)
-      : mine(smem_u32(rows) + (uint32_t)tid * V * sizeof(T)), full(smem_u32(&sh->full[0])), empty(smem_u32(&sh->empty[0])),
-        q(0u), lane0((tid & 31) == 0) {}
-  __device__ __forceinline__ Vec<T, V> get(int& slot) {
-    slot = (int)(q & (kRing - 1));
-    mbar_wait_s(full + (uint32_t)slot * 8u, (q / kRing) & 1u);
-    ++q;
-    return lds_vec_s<T, V>(mine + (uint32_t)slot * (uint32_t)(P * sizeof(T)));
+  __device__ __forceinline__ RingConsumer(const unsigned char* rows, RingShared* sh, int tid, int slots)
+      : mine(smem_u32(rows) + (uint32_t)tid * 16u), full(smem_u32(&sh->full[0])), empty(smem_u32(&sh->empty[0])),
+        slot(0u), parity(0u), n_slots((uint32_t)slots), lane0((tid & 31) == 0) {}
+  __device__ __forceinline__ Vec<T, V> get(uint32_t& used) {
+    used = slot;
+    mbar_wait_s(full + slot * 8u, parity);
+    const Vec<T, V> x = lds_vec_s<T, V>(mine + slot * (uint32_t)kRingRowBytes);
+    if (++slot == n_slots) {
+      slot = 0u;
+      parity ^= 1u;
+    }
+    return x;
   }
-  __device__ __forceinline__ void release(int slot) {
+  __device__ __forceinline__ void release(uint32_t used) {
     __syncwarp();
-    if (lane0) mbar_arrive_s(empty + (uint32_t)slot * 8u);
+    if (lane0) mbar_arrive_s(empty + used * 8u);
   }
 };
 
+// The producer warp runs converged (uniform counters and addresses, us_tma.cuh); only the two
+// instructions that post the byte count and issue the copy are predicated on the elected lane.
 struct RingProducer {
   RingShared* sh;
-  uint32_t q;
+  unsigned char* rows;
+  uint32_t slot, round, n_slots;
+  bool leader;
   template <typename T>
-  __device__ __forceinline__ void put(T* rows, int P, const T* src, uint64_t policy) {
-    const int slot = (int)(q & (kRing - 1));
-    if (q >= (uint32_t)kRing) mbar_wait(&sh->empty[slot], ((q / kRing) - 1u) & 1u);
-    const uint32_t bytes = (uint32_t)(P * sizeof(T));
-    mbar_arrive_expect_tx(&sh->full[slot], bytes);
-    tma_load_row(rows + (size_t)slot * P, src, bytes, &sh->full[slot], policy);
-    ++q;
+  __device__ __forceinline__ void put(const T* src, uint64_t policy) {
+    if (round > 0u) {
+      // one lane polls, the warp reconverges behind it: the copy below is a warp-level (uniform
+      // datapath) instruction and must be reached exactly once per row
+      if (leader) mbar_wait_one(&sh->empty[slot], (round - 1u) & 1u);
+      __syncwarp();
+    }
+    if (leader) {
+      mbar_arrive_expect_tx(&sh->full[slot], (uint32_t)kRingRowBytes);
+      tma_load_row(rows + (size_t)slot * kRingRowBytes, src, (uint32_t)kRingRowBytes, &sh->full[slot], policy);
+    }
+    if (++slot == n_slots) {
+      slot = 0u;
+      ++round;
+    }
   }
 };
 
-__device__ __forceinline__ void ring_init(RingShared* sh) {
+__device__ __forceinline__ RingShared* ring_init(unsigned char* smem_raw, int n_slots) {
+  RingShared* sh = reinterpret_cast<RingShared*>(smem_raw);
   if (threadIdx.x == 0) {
-#pragma unroll
-    for (int s = 0; s < kRing; ++s) {
+    for (int s = 0; s < n_slots; ++s) {
       mbar_init(&sh->full[s], 1);
       mbar_init(&sh->empty[s], kRingConsumers / 32);
     }
     fence_mbar_init();
   }
   __syncthreads();
+  return sh;
+}
+
+// the parking rows: thread-private columns, plain shared-memory accesses
+template <typename T, int V>
+__device__ __forceinline__ void park_store(uint32_t addr, const Vec<T, V>& x) {
+  uint32_t w[4];
+  memcpy(w, &x, 16);
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
 }
 
 // =================================================================================================
 template <typename T, int V>
-__global__ void __launch_bounds__(kRingBlock, 3) to_cartesian_ring(const __grid_constant__ XformParams p, int64_t n_tiles) {
+__global__ void __launch_bounds__(kRingBlock, 3) to_cartesian_ring(const __grid_constant__ RingParams p, int64_t n_tiles, int n_slots) {
+  static_assert(sizeof(T) * V == 16, "ring rows are 16 bytes per thread");
   constexpr int P = kRingConsumers * V;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  T* rows = reinterpret_cast<T*>(smem_raw);
-  RingShared* sh = reinterpret_cast<RingShared*>(smem_raw + (size_t)kRing * P * sizeof(T));
-  ring_init(sh);
-  const int nn = p.plan.n_nodes;
-  const bool has_r = p.r_in != nullptr;
+  RingShared* sh = ring_init(smem_raw, n_slots);
+  unsigned char* rows = smem_raw + kRingHeader;
+  const int nn = p.n_nodes;
+  const bool has_r = p.has_r != 0;
   const int tid = threadIdx.x;
-  if (tid >= kRingConsumers) {
-    if (tid != kRingConsumers) return;
+  if (warp_index_uniform() == kRingConsumers / 32) {
     const uint64_t policy = policy_evict_first();
-    RingProducer prod{sh, 0u};
+    RingProducer prod{sh, rows, 0u, 0u, (uint32_t)n_slots, elect_one()};
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t first = tile * P;
-      if (has_r) prod.put<T>(rows, P, (const T*)p.r_in + first, policy);
+      if (has_r) prod.put<T>((const T*)p.in[nn] + first, policy);
 #pragma unroll 1
-      for (int k = 0; k < nn; ++k) prod.put<T>(rows, P, (const T*)p.in[node_slot(p.plan.node[k])] + first, policy);
+      for (int k = 0; k < nn; ++k) prod.put<T>((const T*)p.in[p.d[k].row_a] + first, policy);
     }
     return;
   }
-  RingConsumer<T, V> ring(rows, sh, tid);
+  RingConsumer<T, V> ring(rows, sh, tid, n_slots);
+  const uint32_t park = smem_u32(rows) + (uint32_t)n_slots * (uint32_t)kRingRowBytes + (uint32_t)tid * 16u;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t g = tile * P + (int64_t)tid * V;
     Vec<T, V> cur;
     if (has_r) {
-      int slot;
+      uint32_t slot;
       cur = ring.get(slot);
       // the row is in registers once it has been used; `cur` is consumed by the first product
       // below, but the slot can go back right away: force the use with a register barrier
@@ -116,24 +149,22 @@ __global__ void __launch_bounds__(kRingBlock, 3) to_cartesian_ring(const __grid_
 #pragma unroll
       for (int v = 0; v < V; ++v) cur.v[v] = T(1);
     }
-    Vec<T, V> stack[US_MAX_STACK];
-    int sp = 0;
     for (int k = 0; k < nn; ++k) {
-      const uint64_t w = p.plan.node[k];
-      int slot;
+      const NodeDesc& d = p.d[k];
+      uint32_t slot;
       const Vec<T, V> th = ring.get(slot);
       Vec<T, V> pc, ps, sn, cs;
       sincos_vec<V>(th.v, sn.v, cs.v);
       ring.release(slot);  // after the sincos consumed the angles
       mul_vec<V>(cur.v, cs.v, pc.v);
       mul_vec<V>(cur.v, sn.v, ps.v);
-      const int kind = node_kind(w);
-      T* const oc = (kind == US_NODE_A || kind == US_NODE_B) ? (T*)p.out[node_cos_leaf(w)] : nullptr;
-      T* const os = (kind == US_NODE_A || kind == US_NODE_BP) ? (T*)p.out[node_sin_leaf(w)] : nullptr;
-      if (kind == US_NODE_C) stack[sp++] = ps;
+      const uint32_t kind = d.kind;
+      if ((kind & kNodeKindMask) == US_NODE_C) park_store<T, V>(park + d.park, ps);
 #pragma unroll
-      for (int v = 0; v < V; ++v) cur.v[v] = (kind == US_NODE_B) ? ps.v[v] : pc.v[v];
-      if (kind == US_NODE_A && sp > 0) cur = stack[--sp];
+      for (int v = 0; v < V; ++v) cur.v[v] = ((kind & kNodeKindMask) == US_NODE_B) ? ps.v[v] : pc.v[v];
+      if (kind & kNodeLinked) cur = lds_vec_s<T, V>(park + d.park);
+      T* const oc = (T*)d.out_a;
+      T* const os = (T*)d.out_b;
       if (oc) stg_vec<T, V>(oc + g, pc);
       if (os) stg_vec<T, V>(os + g, ps);
     }
@@ -142,43 +173,43 @@ __global__ void __launch_bounds__(kRingBlock, 3) to_cartesian_ring(const __grid_
 
 // =================================================================================================
 template <typename T, int V>
-__global__ void __launch_bounds__(kRingBlock, 3) from_cartesian_ring(const __grid_constant__ XformParams p, int64_t n_tiles) {
+__global__ void __launch_bounds__(kRingBlock, 3) from_cartesian_ring(const __grid_constant__ RingParams p, int64_t n_tiles, int n_slots) {
+  static_assert(sizeof(T) * V == 16, "ring rows are 16 bytes per thread");
   constexpr int P = kRingConsumers * V;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  T* rows = reinterpret_cast<T*>(smem_raw);
-  RingShared* sh = reinterpret_cast<RingShared*>(smem_raw + (size_t)kRing * P * sizeof(T));
-  ring_init(sh);
-  const int nn = p.plan.n_nodes;
-  const int n_leaves = p.plan.n_leaves;
+  RingShared* sh = ring_init(smem_raw, n_slots);
+  unsigned char* rows = smem_raw + kRingHeader;
+  const int nn = p.n_nodes;
+  const int n_leaves = p.n_rows;
   T* const r_out = (T*)p.r_out;
   const int tid = threadIdx.x;
-  if (tid >= kRingConsumers) {
-    if (tid != kRingConsumers) return;
+  if (warp_index_uniform() == kRingConsumers / 32) {
     const uint64_t keep = policy_evict_last(), drop = policy_evict_first();
-    RingProducer prod{sh, 0u};
+    RingProducer prod{sh, rows, 0u, 0u, (uint32_t)n_slots, elect_one()};
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t first = tile * P;
       if (r_out) {
 #pragma unroll 1
-        for (int l = 0; l < n_leaves; ++l) prod.put<T>(rows, P, (const T*)p.in[l] + first, keep);
+        for (int l = 0; l < n_leaves; ++l) prod.put<T>((const T*)p.in[l] + first, keep);
       }
 #pragma unroll 1
       for (int k = nn - 1; k >= 0; --k) {
-        const uint64_t w = p.plan.node[k];
-        const int kind = node_kind(w);
-        if (kind == US_NODE_A || kind == US_NODE_B) prod.put<T>(rows, P, (const T*)p.in[node_cos_leaf(w)] + first, drop);
-        if (kind == US_NODE_A || kind == US_NODE_BP) prod.put<T>(rows, P, (const T*)p.in[node_sin_leaf(w)] + first, drop);
+        const NodeDesc& d = p.d[k];
+        const uint32_t kind = d.kind & kNodeKindMask;
+        if (kind == US_NODE_A || kind == US_NODE_B) prod.put<T>((const T*)p.in[d.row_a] + first, drop);
+        if (kind == US_NODE_A || kind == US_NODE_BP) prod.put<T>((const T*)p.in[d.row_b] + first, drop);
       }
     }
     return;
   }
-  RingConsumer<T, V> ring(rows, sh, tid);
+  RingConsumer<T, V> ring(rows, sh, tid, n_slots);
+  const uint32_t park = smem_u32(rows) + (uint32_t)n_slots * (uint32_t)kRingRowBytes + (uint32_t)tid * 16u;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t g = tile * P + (int64_t)tid * V;
     if (r_out) {
       Vec<T, V> acc;
       for (int l = 0; l < n_leaves; ++l) {
-        int slot;
+        uint32_t slot;
         const Vec<T, V> x = ring.get(slot);
         sumsq_step<V>(acc.v, x.v, l == 0);
         ring.release(slot);
@@ -186,18 +217,17 @@ __global__ void __launch_bounds__(kRingBlock, 3) from_cartesian_ring(const __gri
       sqrt_vec<V>(acc.v);
       stg_vec<T, V>(r_out + g, acc);
     }
-    Vec<T, V> stack[US_MAX_STACK];
-    int sp = 0;
     Vec<T, V> cur;
 #pragma unroll
     for (int v = 0; v < V; ++v) cur.v[v] = T(0);
     for (int k = nn - 1; k >= 0; --k) {
-      const uint64_t w = p.plan.node[k];
+      const NodeDesc& d = p.d[k];
+      const uint32_t kind = d.kind;
       Vec<T, V> th, nxt;
-      switch (node_kind(w)) {  // one specialised body per node kind (see from_cartesian_tiled)
+      switch (kind & kNodeKindMask) {  // one specialised body per node kind (see from_cartesian_tiled)
         case US_NODE_A: {
-          if (k != nn - 1) stack[sp++] = cur;
-          int slot_c, slot_s;
+          if (kind & kNodeLinked) park_store<T, V>(park + d.park, cur);
+          uint32_t slot_c, slot_s;
           const Vec<T, V> vc = ring.get(slot_c);
           const Vec<T, V> vs = ring.get(slot_s);
           node_from_vec<V, false, false>(vs.v, vc.v, th.v, nxt.v);
@@ -206,27 +236,27 @@ __global__ void __launch_bounds__(kRingBlock, 3) from_cartesian_ring(const __gri
           break;
         }
         case US_NODE_B: {
-          int slot_c;
+          uint32_t slot_c;
           const Vec<T, V> vc = ring.get(slot_c);
           node_from_vec<V, true, false>(cur.v, vc.v, th.v, nxt.v);
           ring.release(slot_c);
           break;
         }
         case US_NODE_BP: {
-          int slot_s;
+          uint32_t slot_s;
           const Vec<T, V> vs = ring.get(slot_s);
           node_from_vec<V, false, true>(vs.v, cur.v, th.v, nxt.v);
           ring.release(slot_s);
           break;
         }
         default: {
-          const Vec<T, V> vs = stack[--sp];
+          const Vec<T, V> vs = lds_vec_s<T, V>(park + d.park);
           node_from_vec<V, true, true>(vs.v, cur.v, th.v, nxt.v);
           break;
         }
       }
       cur = nxt;
-      T* o = (T*)p.out[node_slot(w)];
+      T* o = (T*)d.out_a;
       if (o) stg_vec<T, V>(o + g, th);
     }
   }
@@ -246,18 +276,24 @@ int launch_ring(const XformParams& p, int dtype, cudaStream_t st, int* points_pe
   *points_per_tile = P;
   const int64_t n_tiles = p.n / P;
   const void* fn = ring_fn<TO>(dtype);
-  const size_t smem = (size_t)kRing * P * esz + sizeof(RingShared);
-  int dev = 0, sms = 148;
-  US_CUDA_TRY(cudaGetDevice(&dev), "cudaGetDevice");
-  US_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute");
+  // three CTAs per SM (75 KB each) as long as the parking rows leave at least 8 ring slots
+  const int park_rows = p.plan.max_stack;
+  int n_slots = (74 * 1024 - kRingHeader) / kRingRowBytes - park_rows;
+  if (n_slots > kMaxRing) n_slots = kMaxRing;
+  if (n_slots < 8) n_slots = 8;
+  const size_t smem = (size_t)kRingHeader + (size_t)(n_slots + park_rows) * kRingRowBytes;
+  if (smem > 227u * 1024u) return kNotTaken;
   int per_sm = 0;
   if (int rc = resident_ctas(fn, smem, kRingBlock, &per_sm)) return rc;
   if (per_sm < 1) return kNotTaken;
-  int64_t grid = (int64_t)sms * per_sm;
+  int64_t grid = (int64_t)sm_count() * per_sm;
   if (grid > n_tiles) grid = n_tiles;
-  XformParams body = p;
+  static RingParams body;  // 10 KB parameter block: filled under a lock, copied by the launch
+  static std::mutex lock;
+  std::lock_guard<std::mutex> guard(lock);
+  if (!build_walk<US_MAX_NODES>(p, TO, 1u, (uint32_t)kRingRowBytes, body)) return kNotTaken;
   int64_t tiles = n_tiles;
-  void* args[] = {(void*)&body, (void*)&tiles};
+  void* args[] = {(void*)&body, (void*)&tiles, (void*)&n_slots};
   US_CUDA_TRY(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(kRingBlock), args, smem, st), "ring launch");
   return 0;
 }

@@ -1,15 +1,27 @@
 // Cartesian <-> polyspherical transforms: contiguous fast path.
 //
-// Persistent, warp-specialised kernels: grid = #SMs x resident CTAs, each CTA = 8 consumer warps
-// + 1 producer warp, looping over tiles of 256*V points.  Each input array contributes one row of
-// a tile; the producer brings rows into shared memory with TMA bulk copies (cp.async.bulk, one
-// per row) that complete on a "full" mbarrier, two stages deep, so a whole tile (tens of KB) is in
-// flight per CTA while the previous one is computed — memory-level parallelism comes from the
-// copy engine, not from registers.  Consumer warps never wait for each other: a warp that has
-// finished reading a stage arrives on that stage's "empty" mbarrier, and only the producer waits
-// for all eight arrivals before refilling it.  Every consumer thread owns V consecutive points:
-// one 128-bit LDS per input row, the compiled pre-order program (kernel-parameter constant bank,
-// warp-uniform control flow), one 128-bit streaming STG per output row.
+// One persistent CTA per SM: one producer warp + G consumer GROUPS of four warps.  A tile is 128*V
+// points (V = 16 bytes / sizeof(T)); each input array contributes one 2 KB row of it.  The tiles
+// of a CTA travel through a pool of S > G shared-memory buffers: the producer brings tile i into
+// buffer i mod S with one TMA bulk copy per row (cp.async.bulk, completing on a "full" mbarrier),
+// group i mod G works on it, and each of the group's warps arrives on the buffer's "empty"
+// mbarrier when it has read what it needs.  "Full" barriers belong to the GROUP, one per tile it
+// may have outstanding (its j-th tile uses barrier j mod 8): successive uses of one buffer go to
+// different groups, and a parity wait on a barrier shared between groups can be satisfied by the
+// wrong phase once the groups drift two uses apart (seen as stale tiles and hangs on the HBM-bound
+// float32 trees); a barrier only one group waits on, in order, cannot alias.  So G tiles are being computed on while S - G
+// tiles are in flight or landed — memory-level parallelism comes from the copy engine and is sized
+// by the shared memory left over, not by registers — and no warp ever waits for a warp of another
+// group.  The pool is cut to the tree: S = what fits in 227 KB, G = as many groups as the register
+// file holds (7 for float32, 6 for float64), fewer for wide trees.
+// (The first version ran 2-3 CTAs of 8 consumer warps with two stages each: trees of 9+ rows fit
+// only two such CTAs, i.e. 4 warps per scheduler for kernels that are latency-bound, and ncu showed
+// 9 % of the warp samples sitting in the full-barrier wait.)
+//
+// Every consumer thread owns V consecutive points: one 128-bit LDS per input row, the node
+// descriptors of us_walk.cuh (kernel-parameter constant bank, warp-uniform control flow), one
+// 128-bit streaming STG per output row.  Deferred branches of `c` nodes are parked in dead rows of
+// the tile (us_walk.cuh): no per-thread stack, no local memory.
 //
 // HBM traffic = algorithmic traffic: every input element is read once, every output written once
 // (2 * c_ndim * sizeof(T) bytes per point and direction).
@@ -22,111 +34,155 @@
 #include "us_common.cuh"
 #include "us_params.cuh"
 #include "us_tma.cuh"
+#include "us_walk.cuh"
 
 namespace us {
 
-constexpr int kTileThreads = 256;                // consumer threads = points per tile / V
-constexpr int kBlockThreads = kTileThreads + 32;  // + one producer warp
-constexpr int kStages = 2;
-// 228 KB of shared memory per SM, 1 KB reserved per CTA: two CTAs of two stages each
-constexpr int kMaxStageBytes = 55 * 1024;
-constexpr int kSmemCeiling = 2 * kMaxStageBytes + 1024;
-
-// Issue the copies of one tile (one elected thread: UBLKCP takes uniform operands, so spreading
-// the rows over lanes would only serialise them again): post the expected byte count, then one
-// bulk copy per input row.
+constexpr int kGroupThreads = 128;  // consumer threads per tile = points per tile / V
+constexpr int kGroupWarps = kGroupThreads / 32;
+constexpr int kMaxBuffers = 32;
+constexpr int kTileCap = 16;              // rows per tile the tile kernels are compiled for
+constexpr int kSmemBytes = 227 * 1024;    // dynamic shared memory one CTA may ask for on sm_100
+constexpr int kRowBytes = kGroupThreads * 16;
+// groups per CTA: 1 + 4 G warps must fit the register file (64 K registers) at the kernels'
+// register counts — float32 <= 64 registers, float64 <= 80
 template <typename T>
-__device__ __forceinline__ void issue_tile(const XformParams& p, int n_rows, bool r_row, T* stage, int P,
-                                           int64_t first_point, uint64_t* bar, uint64_t policy) {
-  const uint32_t row_bytes = (uint32_t)(P * sizeof(T));
-  mbar_arrive_expect_tx(bar, row_bytes * (uint32_t)n_rows);
-  const int n_plain = r_row ? n_rows - 1 : n_rows;
-#pragma unroll 1
-  for (int row = 0; row < n_plain; ++row)
-    tma_load_row(stage + (size_t)row * P, (const T*)p.in[row] + first_point, row_bytes, bar, policy);
-  if (r_row) tma_load_row(stage + (size_t)n_plain * P, (const T*)p.r_in + first_point, row_bytes, bar, policy);
+constexpr int max_groups() { return sizeof(T) == 4 ? 7 : 6; }
+
+using TileParams = WalkParams<kTileCap>;
+
+constexpr int kMaxGroups = 7;
+constexpr int kGroupSlots = 8;  // full barriers per group >= tiles a group can have outstanding + 1 (S / G + 1 <= 8 is checked at launch)
+struct PoolShared {
+  uint64_t full[kMaxGroups][kGroupSlots];  // producer -> group: the bytes of the group's j-th tile have landed (tx count)
+  uint64_t empty[kMaxBuffers];             // group -> producer: its four warps are done with the buffer
+};
+constexpr int kPoolHeader = 1024;
+static_assert(sizeof(PoolShared) <= kPoolHeader, "barrier block");
+static_assert((kGroupSlots & (kGroupSlots - 1)) == 0, "slot count is a power of two");
+
+// The producer warp walks this CTA's tiles with all lanes converged (uniform control flow and
+// addresses), waits until the buffer it is about to overwrite has been released, and its elected
+// lane issues the tile's copies (UBLKCP takes uniform operands; spreading the rows over lanes
+// would only serialise them again).
+template <typename T>
+__device__ __forceinline__ void producer_loop(const TileParams& p, unsigned char* bufs, uint32_t buf_bytes, int n_groups, int n_bufs,
+                                              int64_t n_tiles, PoolShared* sh) {
+  constexpr int P = kGroupThreads * (16 / (int)sizeof(T));
+  const bool leader = elect_one();
+  const uint64_t policy = policy_evict_first();
+  const int n_rows = p.n_rows;
+  int b = 0, g = 0, slot = 0;  // buffer, group and the group's barrier slot of the current tile
+  uint32_t round = 0;          // how many times the pool has wrapped
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    if (round > 0) {
+      // one lane polls, the warp reconverges behind it: the copies below are warp-level (uniform
+      // datapath) instructions and must be reached exactly once per tile
+      if (leader) mbar_wait_one(&sh->empty[b], (round - 1u) & 1u);
+      __syncwarp();
+    }
+    unsigned char* dst = bufs + (size_t)b * buf_bytes;
+    uint64_t* bar = &sh->full[g][slot];
+    if (leader) mbar_arrive_expect_tx(bar, (uint32_t)n_rows * (uint32_t)kRowBytes);
+    const int64_t first = tile * P;
+#pragma unroll 4
+    for (int row = 0; row < n_rows; ++row) {
+      const T* src = (const T*)p.in[row] + first;
+      if (leader) tma_load_row(dst + (size_t)row * kRowBytes, src, (uint32_t)kRowBytes, bar, policy);
+    }
+    if (++b == n_bufs) {
+      b = 0;
+      ++round;
+    }
+    if (++g == n_groups) {
+      g = 0;
+      slot = (slot + 1) & (kGroupSlots - 1);
+    }
+  }
 }
 
-struct TileShared {
-  uint64_t full[kStages];   // producer -> consumers: the stage's bytes have landed (tx count)
-  uint64_t empty[kStages];  // consumers -> producer: all 8 consumer warps are done with the stage
+// Writes to shared memory by the consumers (parked branches) must be ordered before the TMA unit
+// overwrites the buffer with the next tile: generic proxy -> async proxy.
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <typename T, int V>
+__device__ __forceinline__ Vec<T, V> lds_at(const unsigned char* mine, uint32_t row_off) {
+  return *reinterpret_cast<const Vec<T, V>*>(mine + row_off);
+}
+template <typename T, int V>
+__device__ __forceinline__ void sts_at(unsigned char* mine, uint32_t row_off, const Vec<T, V>& x) {
+  *reinterpret_cast<Vec<T, V>*>(mine + row_off) = x;
+}
+
+// Position of a consumer group in the tile sequence of its CTA: its j-th tile is tile
+// blockIdx + (group + j G) gridDim, sits in buffer (group + j G) mod S and is announced on the
+// group's barrier j mod kGroupSlots, phase parity (j / kGroupSlots) & 1.
+struct TileCursor {
+  int64_t tile;
+  int b, slot;
+  uint32_t parity;
+  __device__ __forceinline__ TileCursor(int group) : tile((int64_t)blockIdx.x + (int64_t)group * gridDim.x), b(group), slot(0), parity(0u) {}
+  __device__ __forceinline__ void next(int n_groups, int n_bufs) {
+    tile += (int64_t)n_groups * gridDim.x;
+    b += n_groups;  // n_groups < n_bufs: at most one wrap
+    if (b >= n_bufs) b -= n_bufs;
+    if (++slot == kGroupSlots) {
+      slot = 0;
+      parity ^= 1u;
+    }
+  }
 };
 
-__device__ __forceinline__ void init_barriers(TileShared* sh) {
+__device__ __forceinline__ PoolShared* pool_init(unsigned char* smem_raw, int n_groups, int n_bufs) {
+  PoolShared* sh = reinterpret_cast<PoolShared*>(smem_raw);
   if (threadIdx.x == 0) {
-#pragma unroll
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(&sh->full[s], 1);
-      mbar_init(&sh->empty[s], kTileThreads / 32);
-    }
+    for (int g = 0; g < n_groups; ++g)
+      for (int s = 0; s < kGroupSlots; ++s) mbar_init(&sh->full[g][s], 1);
+    for (int s = 0; s < n_bufs; ++s) mbar_init(&sh->empty[s], kGroupWarps);
     fence_mbar_init();
   }
   __syncthreads();
+  return sh;
 }
-
-// The producer warp: one elected lane walks this CTA's tiles, waits until the stage it is about to
-// overwrite has been released, and issues the tile's copies.
-template <typename T>
-__device__ __forceinline__ void producer_loop(const XformParams& p, int n_rows, bool r_row, T* stage0, size_t stage_elems,
-                                              int P, int64_t n_tiles, TileShared* sh) {
-  if ((threadIdx.x & 31) != 0) return;
-  const uint64_t policy = policy_evict_first();
-  int it = 0;
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-    const int s = it % kStages;
-    if (it >= kStages) mbar_wait(&sh->empty[s], (uint32_t)(((it / kStages) - 1) & 1));
-    issue_tile<T>(p, n_rows, r_row, stage0 + s * stage_elems, P, tile * P, &sh->full[s], policy);
-  }
-}
-
-// A consumer warp is done with a stage: order its shared-memory reads, then one arrival.
-__device__ __forceinline__ void release_stage(TileShared* sh, int s) {
-  __syncwarp();
-  if ((threadIdx.x & 31) == 0) mbar_arrive(&sh->empty[s]);
-}
-
 
 // =================================================================================================
 // to_cartesian
 // =================================================================================================
-template <typename T, int V, bool STACK>
-__global__ void __launch_bounds__(kBlockThreads, 2) to_cartesian_tiled(const __grid_constant__ XformParams p, int64_t n_tiles) {
-  constexpr int P = kTileThreads * V;
+template <typename T, int V>
+__global__ void __launch_bounds__(32 + kGroupThreads * max_groups<T>(), 1)
+    to_cartesian_tiled(const __grid_constant__ TileParams p, int64_t n_tiles, int n_groups, int n_bufs) {
+  constexpr int P = kGroupThreads * V;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int nn = p.plan.n_nodes;
-  const bool has_r = p.r_in != nullptr;
-  const int n_rows = nn + (has_r ? 1 : 0);
-  T* stage0 = reinterpret_cast<T*>(smem_raw);
-  const size_t stage_elems = (size_t)n_rows * P;
-  TileShared* sh = reinterpret_cast<TileShared*>(smem_raw + kStages * stage_elems * sizeof(T));
-  init_barriers(sh);
+  PoolShared* sh = pool_init(smem_raw, n_groups, n_bufs);
+  unsigned char* bufs = smem_raw + kPoolHeader;
+  const int nn = p.n_nodes;
+  const uint32_t buf_bytes = (uint32_t)p.n_rows * (uint32_t)kRowBytes;
   const int tid = threadIdx.x;
-  if (tid >= kTileThreads) {
-    producer_loop<T>(p, n_rows, has_r, stage0, stage_elems, P, n_tiles, sh);
+  const int warp = warp_index_uniform();
+  if (warp == 0) {
+    producer_loop<T>(p, bufs, buf_bytes, n_groups, n_bufs, n_tiles, sh);
     return;
   }
-  int it = 0;
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-    const int s = it % kStages;
-    const T* stage = stage0 + s * stage_elems;
-    mbar_wait(&sh->full[s], (uint32_t)((it / kStages) & 1));
-    const int64_t g = tile * P + (int64_t)tid * V;
+  const int t = (tid - 32) & (kGroupThreads - 1);
+  const bool has_r = p.has_r != 0;
+  const int group = (warp - 1) / kGroupWarps;
+  for (TileCursor at(group); at.tile < n_tiles; at.next(n_groups, n_bufs)) {
+    unsigned char* mine = bufs + (size_t)at.b * buf_bytes + t * 16;
+    mbar_wait(&sh->full[group][at.slot], at.parity);
+    const int64_t g = at.tile * P + (int64_t)t * V;
     Vec<T, V> cur;
     if (has_r) {
-      cur = lds_vec<T, V>(stage + (size_t)nn * P, tid);
+      cur = lds_at<T, V>(mine, (uint32_t)nn * kRowBytes);
     } else {
 #pragma unroll
       for (int v = 0; v < V; ++v) cur.v[v] = T(1);
     }
-    Vec<T, V> stack[STACK ? US_MAX_STACK : 1];
-    int sp = 0;
-    uint64_t w = p.plan.node[0];
-    Vec<T, V> th = lds_vec<T, V>(stage + (size_t)node_slot(w) * P, tid);
-#pragma unroll(sizeof(T) == 4 ? 1 : 2)  // A/B on one box: float32 1 % faster without unrolling, float64 2-4 % faster with 2
+    Vec<T, V> th = lds_at<T, V>(mine, p.d[0].row_a);
+#pragma unroll(sizeof(T) == 4 ? 1 : 2)
     for (int k = 0; k < nn; ++k) {
-      // fetch the next node's word and angles before the long sincos chains of this one
-      const uint64_t w_next = p.plan.node[(k + 1 < nn) ? k + 1 : k];
-      const Vec<T, V> th_next = lds_vec<T, V>(stage + (size_t)node_slot(w_next) * P, tid);
+      const NodeDesc& d = p.d[k];
+      // fetch the next node's angles before the long sincos chains of this one
+      const Vec<T, V> th_next = lds_at<T, V>(mine, p.d[(k + 1 < nn) ? k + 1 : k].row_a);
       Vec<T, V> pc, ps, sn, cs;
       sincos_vec<V>(th.v, sn.v, cs.v);
       mul_vec<V>(cur.v, cs.v, pc.v);
@@ -134,24 +190,21 @@ __global__ void __launch_bounds__(kBlockThreads, 2) to_cartesian_tiled(const __g
       // data-flow form of the four node kinds (all predicates are warp-uniform):
       //   a : both products are leaves, resume the most recently deferred branch
       //   b : cos product is a leaf, continue along sin      b': sin product is a leaf, continue along cos
-      //   c : defer the sin product, continue along cos
-      const int kind = node_kind(w);
-      T* const oc = (kind == US_NODE_A || kind == US_NODE_B) ? (T*)p.out[node_cos_leaf(w)] : nullptr;
-      T* const os = (kind == US_NODE_A || kind == US_NODE_BP) ? (T*)p.out[node_sin_leaf(w)] : nullptr;
-      if constexpr (STACK) {
-        if (kind == US_NODE_C) stack[sp++] = ps;
-      }
+      //   c : park the sin product, continue along cos
+      const uint32_t kind = d.kind;
+      if ((kind & kNodeKindMask) == US_NODE_C) sts_at<T, V>(mine, d.park, ps);
 #pragma unroll
-      for (int v = 0; v < V; ++v) cur.v[v] = (kind == US_NODE_B) ? ps.v[v] : pc.v[v];
-      if constexpr (STACK) {
-        if (kind == US_NODE_A && sp > 0) cur = stack[--sp];
-      }
+      for (int v = 0; v < V; ++v) cur.v[v] = ((kind & kNodeKindMask) == US_NODE_B) ? ps.v[v] : pc.v[v];
+      if (kind & kNodeLinked) cur = lds_at<T, V>(mine, d.park);
+      T* const oc = (T*)d.out_a;
+      T* const os = (T*)d.out_b;
       if (oc) stg_vec<T, V>(oc + g, pc);
       if (os) stg_vec<T, V>(os + g, ps);
-      w = w_next;
       th = th_next;
     }
-    release_stage(sh, s);
+    if (p.max_park) fence_proxy_async();
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(&sh->empty[at.b]);
   }
 }
 
@@ -162,33 +215,34 @@ __global__ void __launch_bounds__(kBlockThreads, 2) to_cartesian_tiled(const __g
 // (create_standard_prime): every node but the last has one leaf operand and the running norm as the
 // other, so the walk needs no kind switch, no operand selection, and the atan2 can skip the sign
 // logic of the operand that is known to be a norm.
-template <typename T, int V, bool STACK, int CHAIN>
-__global__ void __launch_bounds__(kBlockThreads, sizeof(T) == 8 ? 3 : 2) from_cartesian_tiled(const __grid_constant__ XformParams p, int64_t n_tiles) {
-  constexpr int P = kTileThreads * V;
+template <typename T, int V, int CHAIN>
+__global__ void __launch_bounds__(32 + kGroupThreads * max_groups<T>(), 1)
+    from_cartesian_tiled(const __grid_constant__ TileParams p, int64_t n_tiles, int n_groups, int n_bufs) {
+  constexpr int P = kGroupThreads * V;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int nn = p.plan.n_nodes;
-  const int n_rows = p.plan.n_leaves;
-  T* stage0 = reinterpret_cast<T*>(smem_raw);
-  const size_t stage_elems = (size_t)n_rows * P;
-  TileShared* sh = reinterpret_cast<TileShared*>(smem_raw + kStages * stage_elems * sizeof(T));
-  init_barriers(sh);
+  PoolShared* sh = pool_init(smem_raw, n_groups, n_bufs);
+  unsigned char* bufs = smem_raw + kPoolHeader;
+  const int nn = p.n_nodes;
+  const int n_rows = p.n_rows;
+  const uint32_t buf_bytes = (uint32_t)n_rows * (uint32_t)kRowBytes;
   const int tid = threadIdx.x;
-  if (tid >= kTileThreads) {
-    producer_loop<T>(p, n_rows, false, stage0, stage_elems, P, n_tiles, sh);
+  const int warp = warp_index_uniform();
+  if (warp == 0) {
+    producer_loop<T>(p, bufs, buf_bytes, n_groups, n_bufs, n_tiles, sh);
     return;
   }
+  const int t = (tid - 32) & (kGroupThreads - 1);
   T* const r_out = (T*)p.r_out;
-  int it = 0;
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-    const int s = it % kStages;
-    const T* stage = stage0 + s * stage_elems;
-    mbar_wait(&sh->full[s], (uint32_t)((it / kStages) & 1));
-    const int64_t g = tile * P + (int64_t)tid * V;
+  const int group = (warp - 1) / kGroupWarps;
+  for (TileCursor at(group); at.tile < n_tiles; at.next(n_groups, n_bufs)) {
+    unsigned char* mine = bufs + (size_t)at.b * buf_bytes + t * 16;
+    mbar_wait(&sh->full[group][at.slot], at.parity);
+    const int64_t g = at.tile * P + (int64_t)t * V;
     if (r_out) {
       // leaves in c_nodes order, sequential, each square and each add rounded once
       Vec<T, V> acc;
       for (int l = 0; l < n_rows; ++l) {
-        const Vec<T, V> x = lds_vec<T, V>(stage + (size_t)l * P, tid);
+        const Vec<T, V> x = lds_at<T, V>(mine, (uint32_t)l * kRowBytes);
         sumsq_step<V>(acc.v, x.v, l == 0);
       }
       sqrt_vec<V>(acc.v);
@@ -197,71 +251,68 @@ __global__ void __launch_bounds__(kBlockThreads, sizeof(T) == 8 ? 3 : 2) from_ca
     Vec<T, V> cur;
     if constexpr (CHAIN != 0) {
       {
-        const uint64_t w = p.plan.node[nn - 1];  // the closing `a` node: two leaves
-        const Vec<T, V> vc = lds_vec<T, V>(stage + (size_t)node_cos_leaf(w) * P, tid);
-        const Vec<T, V> vs = lds_vec<T, V>(stage + (size_t)node_sin_leaf(w) * P, tid);
+        const NodeDesc& d = p.d[nn - 1];  // the closing `a` node: two leaves
+        const Vec<T, V> vc = lds_at<T, V>(mine, d.row_a);
+        const Vec<T, V> vs = lds_at<T, V>(mine, d.row_b);
         Vec<T, V> th;
         node_from_vec<V>(vs.v, vc.v, th.v, cur.v);
-        T* o = (T*)p.out[node_slot(w)];
+        T* o = (T*)d.out_a;
         if (o) stg_vec<T, V>(o + g, th);
       }
 #pragma unroll 2
       for (int k = nn - 2; k >= 0; --k) {
-        const uint64_t w = p.plan.node[k];
-        const int leaf_row = (CHAIN == 1) ? node_cos_leaf(w) : node_sin_leaf(w);
-        const Vec<T, V> leaf = lds_vec<T, V>(stage + (size_t)leaf_row * P, tid);
+        const NodeDesc& d = p.d[k];
+        const Vec<T, V> leaf = lds_at<T, V>(mine, CHAIN == 1 ? d.row_a : d.row_b);
         Vec<T, V> th, nxt;
         if constexpr (CHAIN == 1)
           node_from_vec<V, true, false>(cur.v, leaf.v, th.v, nxt.v);  // theta = atan2(norm, leaf)
         else
           node_from_vec<V, false, true>(leaf.v, cur.v, th.v, nxt.v);  // theta = atan2(leaf, norm)
         cur = nxt;
-        T* o = (T*)p.out[node_slot(w)];
+        T* o = (T*)d.out_a;
         if (o) stg_vec<T, V>(o + g, th);
       }
     } else {
       // Any tree: one specialised body per node kind (warp-uniform switch), so that no operand has
       // to be selected at run time and the atan2 can drop the sign logic of operands that are norms.
-      Vec<T, V> stack[STACK ? US_MAX_STACK : 1];
-      int sp = 0;
 #pragma unroll
       for (int v = 0; v < V; ++v) cur.v[v] = T(0);
       for (int k = nn - 1; k >= 0; --k) {
-        const uint64_t w = p.plan.node[k];
+        const NodeDesc& d = p.d[k];
+        const uint32_t kind = d.kind;
         Vec<T, V> th, nxt;
-        switch (node_kind(w)) {
-          case US_NODE_A: {  // two leaves; a finished sibling subtree waits for its `c` parent
-            if constexpr (STACK) {
-              if (k != nn - 1) stack[sp++] = cur;
-            }
-            const Vec<T, V> vc = lds_vec<T, V>(stage + (size_t)node_cos_leaf(w) * P, tid);
-            const Vec<T, V> vs = lds_vec<T, V>(stage + (size_t)node_sin_leaf(w) * P, tid);
+        switch (kind & kNodeKindMask) {
+          case US_NODE_A: {  // two leaves; a finished sibling subtree waits, parked, for its `c` parent
+            const Vec<T, V> vc = lds_at<T, V>(mine, d.row_a);
+            const Vec<T, V> vs = lds_at<T, V>(mine, d.row_b);
+            if (kind & kNodeLinked) sts_at<T, V>(mine, d.park, cur);
             node_from_vec<V, false, false>(vs.v, vc.v, th.v, nxt.v);
             break;
           }
           case US_NODE_B: {  // cos child leaf, sin child = running norm (>= 0)
-            const Vec<T, V> vc = lds_vec<T, V>(stage + (size_t)node_cos_leaf(w) * P, tid);
+            const Vec<T, V> vc = lds_at<T, V>(mine, d.row_a);
             node_from_vec<V, true, false>(cur.v, vc.v, th.v, nxt.v);
             break;
           }
           case US_NODE_BP: {  // sin child leaf, cos child = running norm (>= 0)
-            const Vec<T, V> vs = lds_vec<T, V>(stage + (size_t)node_sin_leaf(w) * P, tid);
+            const Vec<T, V> vs = lds_at<T, V>(mine, d.row_b);
             node_from_vec<V, false, true>(vs.v, cur.v, th.v, nxt.v);
             break;
           }
-          default: {  // both children internal: cos = running norm, sin = the deferred norm
-            Vec<T, V> vs = cur;
-            if constexpr (STACK) vs = stack[--sp];
+          default: {  // both children internal: cos = running norm, sin = the parked norm
+            const Vec<T, V> vs = lds_at<T, V>(mine, d.park);
             node_from_vec<V, true, true>(vs.v, cur.v, th.v, nxt.v);
             break;
           }
         }
         cur = nxt;
-        T* o = (T*)p.out[node_slot(w)];
+        T* o = (T*)d.out_a;
         if (o) stg_vec<T, V>(o + g, th);
       }
+      if (p.max_park) fence_proxy_async();
     }
-    release_stage(sh, s);
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(&sh->empty[at.b]);
   }
 }
 
@@ -270,29 +321,13 @@ __global__ void __launch_bounds__(kBlockThreads, sizeof(T) == 8 ? 3 : 2) from_ca
 // =================================================================================================
 static bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
 
-struct Variant {
-  const void* fn;
-  int v;
-};
-
-template <typename T, int V>
-static const void* variant(bool to, bool stack, int chain) {
-  if (to) return stack ? (const void*)&to_cartesian_tiled<T, V, true> : (const void*)&to_cartesian_tiled<T, V, false>;
-  if (stack) return (const void*)&from_cartesian_tiled<T, V, true, 0>;
-  if (chain == 1) return (const void*)&from_cartesian_tiled<T, V, false, 1>;
-  if (chain == 2) return (const void*)&from_cartesian_tiled<T, V, false, 2>;
-  return (const void*)&from_cartesian_tiled<T, V, false, 0>;
-}
-
-template <bool TO>
-static const void* pick(int dtype, int v, bool stack, int chain) {
-  if (dtype == US_F32) {
-    if (v == 4) return variant<float, 4>(TO, stack, chain);
-    if (v == 2) return variant<float, 2>(TO, stack, chain);
-    return variant<float, 1>(TO, stack, chain);
-  }
-  if (v == 2) return variant<double, 2>(TO, stack, chain);
-  return variant<double, 1>(TO, stack, chain);
+template <typename T>
+static const void* variant(bool to, int chain) {
+  constexpr int V = 16 / (int)sizeof(T);
+  if (to) return (const void*)&to_cartesian_tiled<T, V>;
+  if (chain == 1) return (const void*)&from_cartesian_tiled<T, V, 1>;
+  if (chain == 2) return (const void*)&from_cartesian_tiled<T, V, 2>;
+  return (const void*)&from_cartesian_tiled<T, V, 0>;
 }
 
 // 1: every node but the last is `b` and the last is `a`; 2: same with `b'`; 0: anything else
@@ -306,14 +341,16 @@ static int chain_kind(const us_plan_t& plan) {
   return first == US_NODE_B ? 1 : 2;
 }
 
-static int sm_count() {
-  static int cached = 0;
-  if (!cached) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) cached = 148;
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (!cached[dev]) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
+    cached[dev] = n;
   }
-  return cached;
+  return cached[dev];
 }
 
 // cudaFuncSetAttribute + the occupancy query cost a few microseconds each; their result only
@@ -322,7 +359,7 @@ int resident_ctas(const void* fn, size_t smem, int block_threads, int* per_sm) {
   struct Entry {
     const void* fn;
     size_t smem;
-    int dev, per_sm;
+    int dev, threads, per_sm;
   };
   static Entry cache[128];
   static int used = 0;
@@ -331,7 +368,7 @@ int resident_ctas(const void* fn, size_t smem, int block_threads, int* per_sm) {
   US_CUDA_TRY(cudaGetDevice(&dev), "cudaGetDevice");
   std::lock_guard<std::mutex> guard(lock);
   for (int i = 0; i < used; ++i)
-    if (cache[i].fn == fn && cache[i].smem == smem && cache[i].dev == dev) {
+    if (cache[i].fn == fn && cache[i].smem == smem && cache[i].dev == dev && cache[i].threads == block_threads) {
       *per_sm = cache[i].per_sm;
       return 0;
     }
@@ -343,12 +380,39 @@ int resident_ctas(const void* fn, size_t smem, int block_threads, int* per_sm) {
     US_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(smem)");
   US_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, fn, block_threads, smem), "occupancy query");
   if (used < 128) {
-    cache[used++] = Entry{fn, smem, dev, *per_sm};
+    cache[used++] = Entry{fn, smem, dev, block_threads, *per_sm};
   } else {
     // table full (128 distinct kernel/tree-width pairs): keep working, just without the shortcut
-    US_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCeiling), "cudaFuncSetAttribute(smem)");
+    US_CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), "cudaFuncSetAttribute(smem)");
   }
   return 0;
+}
+
+static int env_int(const char* name, int fallback) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : fallback;
+}
+
+// Cut the buffer pool to the tree: S buffers of n_rows 2 KB rows in 227 KB, G groups computing, at
+// least two tiles (and ~48 KB) in flight besides.  false: the tree is too wide for tiles.
+static bool pool_geometry(int n_rows, int g_max, int* n_groups, int* n_bufs) {
+  static const int forced_g = env_int("US_TILE_GROUPS", 0), forced_s = env_int("US_TILE_BUFS", 0);  // tuning overrides
+  static const int max_rows = env_int("US_TILE_MAX_ROWS", 13);
+  if (n_rows > max_rows || n_rows > kTileCap + 1) return false;
+  const int buf = n_rows * kRowBytes;
+  int s = (kSmemBytes - kPoolHeader) / buf;
+  if (s > kMaxBuffers) s = kMaxBuffers;
+  int in_flight = (48 * 1024 + buf - 1) / buf;
+  if (in_flight < 2) in_flight = 2;
+  int g = s - in_flight;
+  if (g > g_max) g = g_max;
+  if (forced_g > 0 && forced_g <= g_max) g = forced_g;
+  if (forced_s > 0 && forced_s <= s) s = forced_s;
+  if (g < 2 || s <= g) return false;
+  while ((s + g - 1) / g + 1 > kGroupSlots) --s;  // a group never has more tiles outstanding than barriers to announce them on
+  *n_groups = g;
+  *n_bufs = s;
+  return true;
 }
 
 template <bool TO>
@@ -364,48 +428,33 @@ static int try_tiled(const XformParams& p, int dtype, cudaStream_t st) {
   for (int i = 0; i < n_out; ++i)
     if (p.out[i] && !aligned16(p.out[i])) return kNotTaken;
   if (!TO && p.r_out && !aligned16(p.r_out)) return kNotTaken;
-  // widest vector whose two-stage tile still lets two CTAs share an SM
-  int v = 16 / esz;
-  while (v >= 1 && (int64_t)n_rows * kTileThreads * v * esz > kMaxStageBytes) v >>= 1;
-  {
-    static int forced_v = -1;  // US_TILE_V=<1|2|4>: tuning override (may leave one CTA per SM)
-    if (forced_v < 0) {
-      const char* e = getenv("US_TILE_V");
-      forced_v = e ? atoi(e) : 0;
-    }
-    if (forced_v > 0 && forced_v <= 16 / esz) v = forced_v;
-  }
-  int P = kTileThreads * v;
-  int64_t n_tiles = v >= 1 ? p.n / P : 0;
-  if (v < 16 / esz) {
-    // wide tree: full-width vectors through the row ring instead of narrower resident tiles
-    const int ring_p = kTileThreads * (16 / esz);
+  int P = kGroupThreads * (16 / esz);
+  int64_t n_tiles = p.n / P;
+  int n_groups = 0, n_bufs = 0;
+  if (!pool_geometry(n_rows, dtype == US_F32 ? max_groups<float>() : max_groups<double>(), &n_groups, &n_bufs)) {
+    // wide tree: the rows stream through a ring instead of whole tiles being resident
+    const int ring_p = 256 * (16 / esz);
     if (p.n / ring_p < 2 * sm_count()) return kNotTaken;
     const int rc = launch_ring<TO>(p, dtype, st, &P);
     if (rc != 0) return rc;
     n_tiles = p.n / P;
   } else {
-  {
-    static int64_t min_tiles = -1;  // US_TILED_MIN_TILES=<n>: tuning override of the small-batch cut-over
-    if (min_tiles < 0) {
-      const char* e = getenv("US_TILED_MIN_TILES");
-      min_tiles = e ? atoll(e) : 4 * sm_count();
-    }
-    // small batches: below ~4 tiles per SM the pipeline's fill/drain costs more than it hides
-    // (measured under CUDA-graph replay, create_spherical float64: 3e5 points 7.2 us strided vs 9.9 us tiled)
-    if (n_tiles < min_tiles) return kNotTaken;
-  }
-  const void* fn = pick<TO>(dtype, v, p.plan.max_stack > 0, chain_kind(p.plan));
-  const size_t smem = (size_t)kStages * n_rows * P * esz + sizeof(TileShared);
-  int per_sm = 0;
-  if (int rc = resident_ctas(fn, smem, kBlockThreads, &per_sm)) return rc;
-  if (per_sm < 1) return kNotTaken;
-  int64_t grid = (int64_t)sm_count() * per_sm;
-  if (grid > n_tiles) grid = n_tiles;
-  XformParams body = p;
-  int64_t tiles = n_tiles;
-  void* args[] = {(void*)&body, (void*)&tiles};
-  US_CUDA_TRY(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(kBlockThreads), args, smem, st), "tiled launch");
+    // small batches: below a few tiles per group the pipeline's fill/drain costs more than it hides
+    static const int64_t min_tiles = env_int("US_TILED_MIN_TILES", 8);  // per SM; tuning override
+    if (n_tiles < min_tiles * sm_count()) return kNotTaken;
+    const void* fn = dtype == US_F32 ? variant<float>(TO, chain_kind(p.plan)) : variant<double>(TO, chain_kind(p.plan));
+    const size_t smem = (size_t)kPoolHeader + (size_t)n_bufs * n_rows * kRowBytes;
+    const int threads = 32 + kGroupThreads * n_groups;
+    int per_sm = 0;
+    if (int rc = resident_ctas(fn, smem, threads, &per_sm)) return rc;
+    if (per_sm < 1) return kNotTaken;
+    int64_t grid = sm_count();
+    if (grid > n_tiles) grid = n_tiles;
+    TileParams body;
+    if (!build_walk<kTileCap>(p, TO, (uint32_t)kRowBytes, 0u, body)) return kNotTaken;
+    int64_t tiles = n_tiles;
+    void* args[] = {(void*)&body, (void*)&tiles, (void*)&n_groups, (void*)&n_bufs};
+    US_CUDA_TRY(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3((unsigned)threads), args, smem, st), "tiled launch");
   }
   // ragged tail (< one tile): the strided kernel on the remaining points
   const int64_t done = n_tiles * P;
