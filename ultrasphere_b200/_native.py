@@ -52,6 +52,7 @@ _SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     "us_version": (C.c_char_p, []),
     "us_last_error_string": (C.c_char_p, []),
     "us_device_count": (C.c_int, []),
+    "us_set_tuning": (C.c_int, [C.c_char_p, C.c_int]),
     "us_plan_compile": (
         C.c_int,
         [C.c_int32, C.POINTER(C.c_uint8), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(UsPlan)],

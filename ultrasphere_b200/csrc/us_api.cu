@@ -82,6 +82,11 @@ extern "C" int us_abi_version(void) { return US_ABI_VERSION; }
 extern "C" const char* us_version(void) { return "ultrasphere_b200 0.1.0 (sm_100a)"; }
 extern "C" const char* us_last_error_string(void) { return g_err; }
 
+extern "C" int us_set_tuning(const char* name, int value) {
+  if (!name) return fail(US_EINVAL, "us_set_tuning: null name");
+  return set_tile_tuning(name, value);
+}
+
 extern "C" int us_device_count(void) {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);

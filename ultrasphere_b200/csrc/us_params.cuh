@@ -49,5 +49,6 @@ int launch_ring(const XformParams& p, int dtype, cudaStream_t st, int* points_pe
 // cached cudaFuncSetAttribute(max dynamic smem) + occupancy query
 int resident_ctas(const void* fn, size_t smem, int block_threads, int* per_sm);
 int sm_count();  // of the current device, cached
+int set_tile_tuning(const char* name, int value);
 
 }  // namespace us

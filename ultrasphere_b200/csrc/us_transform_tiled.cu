@@ -28,6 +28,7 @@
 //
 // Reference semantics: src/ultrasphere/_coordinates.py:555-579 (from) and :636-656 (to).
 #include <stdlib.h>
+#include <string.h>
 
 #include <mutex>
 
@@ -208,6 +209,38 @@ __global__ void __launch_bounds__(32 + kGroupThreads * max_groups<T>(), 1)
   }
 }
 
+// The checked walk of a chain for one thread's V points: every node through node_from_vec (fast path
+// where its operands allow, libdevice otherwise — the same per-node choice the generic kernels
+// make, so the values do not depend on which kernel ran).  Out of line: points with zero, tiny,
+// huge or non-finite coordinates only.
+template <typename T, int V, int CHAIN>
+__device__ __noinline__ void chain_redo(const TileParams& p, const unsigned char* mine, int64_t g) {
+  const int nn = p.n_nodes;
+  Vec<T, V> cur;
+  {
+    const NodeDesc& d = p.d[nn - 1];
+    const Vec<T, V> vc = lds_at<T, V>(mine, d.row_a);
+    const Vec<T, V> vs = lds_at<T, V>(mine, d.row_b);
+    Vec<T, V> th;
+    node_from_vec<V>(vs.v, vc.v, th.v, cur.v);
+    T* o = (T*)d.out_a;
+    if (o) stg_vec<T, V>(o + g, th);
+  }
+#pragma unroll 1
+  for (int k = nn - 2; k >= 0; --k) {
+    const NodeDesc& d = p.d[k];
+    const Vec<T, V> leaf = lds_at<T, V>(mine, CHAIN == 1 ? d.row_a : d.row_b);
+    Vec<T, V> th, nxt;
+    if constexpr (CHAIN == 1)
+      node_from_vec<V, true, false>(cur.v, leaf.v, th.v, nxt.v);
+    else
+      node_from_vec<V, false, true>(leaf.v, cur.v, th.v, nxt.v);
+    cur = nxt;
+    T* o = (T*)d.out_a;
+    if (o) stg_vec<T, V>(o + g, th);
+  }
+}
+
 // =================================================================================================
 // from_cartesian
 // =================================================================================================
@@ -250,12 +283,14 @@ __global__ void __launch_bounds__(32 + kGroupThreads * max_groups<T>(), 1)
     }
     Vec<T, V> cur;
     if constexpr (CHAIN != 0) {
+      // fast paths unchecked; one range test per point at the end (us_common.cuh: chain_in_range)
+      Vec<T, V> in_s, in_c;
       {
         const NodeDesc& d = p.d[nn - 1];  // the closing `a` node: two leaves
-        const Vec<T, V> vc = lds_at<T, V>(mine, d.row_a);
-        const Vec<T, V> vs = lds_at<T, V>(mine, d.row_b);
+        in_c = lds_at<T, V>(mine, d.row_a);
+        in_s = lds_at<T, V>(mine, d.row_b);
         Vec<T, V> th;
-        node_from_vec<V>(vs.v, vc.v, th.v, cur.v);
+        node_from_fast_vec<V>(in_s.v, in_c.v, th.v, cur.v);
         T* o = (T*)d.out_a;
         if (o) stg_vec<T, V>(o + g, th);
       }
@@ -265,13 +300,17 @@ __global__ void __launch_bounds__(32 + kGroupThreads * max_groups<T>(), 1)
         const Vec<T, V> leaf = lds_at<T, V>(mine, CHAIN == 1 ? d.row_a : d.row_b);
         Vec<T, V> th, nxt;
         if constexpr (CHAIN == 1)
-          node_from_vec<V, true, false>(cur.v, leaf.v, th.v, nxt.v);  // theta = atan2(norm, leaf)
+          node_from_fast_vec<V, true, false>(cur.v, leaf.v, th.v, nxt.v);  // theta = atan2(norm, leaf)
         else
-          node_from_vec<V, false, true>(leaf.v, cur.v, th.v, nxt.v);  // theta = atan2(leaf, norm)
+          node_from_fast_vec<V, false, true>(leaf.v, cur.v, th.v, nxt.v);  // theta = atan2(leaf, norm)
         cur = nxt;
         T* o = (T*)d.out_a;
         if (o) stg_vec<T, V>(o + g, th);
       }
+      bool ok = true;
+#pragma unroll
+      for (int v = 0; v < V; ++v) ok = ok && chain_in_range(in_s.v[v], in_c.v[v], cur.v[v]);
+      if (!ok) chain_redo<T, V, CHAIN>(p, mine, g);
     } else {
       // Any tree: one specialised body per node kind (warp-uniform switch), so that no operand has
       // to be selected at run time and the atan2 can drop the sign logic of operands that are norms.
@@ -393,12 +432,25 @@ static int env_int(const char* name, int fallback) {
   return e ? atoi(e) : fallback;
 }
 
+// Tuning knobs (none is needed in normal use): environment variables at first use, us_set_tuning()
+// at any time (tools/ab_inproc.py compares settings call by call inside one process, because the
+// HBM-bound kernels drift by several percent over tens of milliseconds on one and the same box).
+struct Tuning {
+  int groups = env_int("US_TILE_GROUPS", 0);        // consumer groups per CTA (0: as many as fit)
+  int bufs = env_int("US_TILE_BUFS", 0);            // buffers in the pool (0: as many as fit)
+  int max_rows = env_int("US_TILE_MAX_ROWS", 13);   // wider trees take the row-ring kernels
+  int min_tiles = env_int("US_TILED_MIN_TILES", 8); // per SM: smaller batches take the strided kernels
+};
+static Tuning& tuning() {
+  static Tuning t;
+  return t;
+}
+
 // Cut the buffer pool to the tree: S buffers of n_rows 2 KB rows in 227 KB, G groups computing, at
 // least two tiles (and ~48 KB) in flight besides.  false: the tree is too wide for tiles.
 static bool pool_geometry(int n_rows, int g_max, int* n_groups, int* n_bufs) {
-  static const int forced_g = env_int("US_TILE_GROUPS", 0), forced_s = env_int("US_TILE_BUFS", 0);  // tuning overrides
-  static const int max_rows = env_int("US_TILE_MAX_ROWS", 13);
-  if (n_rows > max_rows || n_rows > kTileCap + 1) return false;
+  const Tuning& t = tuning();
+  if (n_rows > t.max_rows || n_rows > kTileCap + 1) return false;
   const int buf = n_rows * kRowBytes;
   int s = (kSmemBytes - kPoolHeader) / buf;
   if (s > kMaxBuffers) s = kMaxBuffers;
@@ -406,9 +458,9 @@ static bool pool_geometry(int n_rows, int g_max, int* n_groups, int* n_bufs) {
   if (in_flight < 2) in_flight = 2;
   int g = s - in_flight;
   if (g > g_max) g = g_max;
-  if (forced_g > 0 && forced_g <= g_max) g = forced_g;
-  if (forced_s > 0 && forced_s <= s) s = forced_s;
-  if (g < 2 || s <= g) return false;
+  if (t.groups > 0 && t.groups <= g_max) g = t.groups;
+  if (t.bufs > 0 && t.bufs <= s) s = t.bufs;
+  if (g < 1 || s <= g) return false;
   while ((s + g - 1) / g + 1 > kGroupSlots) --s;  // a group never has more tiles outstanding than barriers to announce them on
   *n_groups = g;
   *n_bufs = s;
@@ -440,8 +492,7 @@ static int try_tiled(const XformParams& p, int dtype, cudaStream_t st) {
     n_tiles = p.n / P;
   } else {
     // small batches: below a few tiles per group the pipeline's fill/drain costs more than it hides
-    static const int64_t min_tiles = env_int("US_TILED_MIN_TILES", 8);  // per SM; tuning override
-    if (n_tiles < min_tiles * sm_count()) return kNotTaken;
+    if (n_tiles < (int64_t)tuning().min_tiles * sm_count()) return kNotTaken;
     const void* fn = dtype == US_F32 ? variant<float>(TO, chain_kind(p.plan)) : variant<double>(TO, chain_kind(p.plan));
     const size_t smem = (size_t)kPoolHeader + (size_t)n_bufs * n_rows * kRowBytes;
     const int threads = 32 + kGroupThreads * n_groups;
@@ -472,6 +523,16 @@ static int try_tiled(const XformParams& p, int dtype, cudaStream_t st) {
     const int rc = TO ? launch_to_cartesian_strided(tail, dtype, st) : launch_from_cartesian_strided(tail, dtype, st);
     if (rc != 0) return rc;
   }
+  return 0;
+}
+
+int set_tile_tuning(const char* name, int value) {
+  Tuning& t = tuning();
+  if (!strcmp(name, "tile_groups")) t.groups = value;
+  else if (!strcmp(name, "tile_bufs")) t.bufs = value;
+  else if (!strcmp(name, "tile_max_rows")) t.max_rows = value;
+  else if (!strcmp(name, "tiled_min_tiles")) t.min_tiles = value;
+  else return fail(US_EINVAL, "us_set_tuning: unknown knob '%s'", name);
   return 0;
 }
 
