@@ -350,3 +350,35 @@ def test_integrate_can_be_captured_in_a_cuda_graph():
     g.replay()
     want = vo.analytic_exp_kx(2 * np.array([0.3, 0.5, 0.2, 0.7]))
     assert abs(out.item() - want) <= 1e-11 * want
+
+
+def test_more_grid_axes_than_one_launch_indexes():
+    """A tree with 13 angles has a 13-axis grid; the fused contraction indexes 12 axes per launch
+    (US_MAX_DIMS), so the host contracts in two passes.  Checked against plain torch arithmetic."""
+    k = 13
+    ext = [2] * (k - 1) + [4]
+    g = torch.Generator(device=DEV).manual_seed(5)
+    val = torch.rand(ext + [3], device=DEV, dtype=torch.float64, generator=g)
+    ws = [torch.rand(e, device=DEV, dtype=torch.float64, generator=g) for e in ext]
+    got = us.weighted_reduce(val, ws)
+    want = val
+    for w in ws:
+        want = torch.tensordot(w, want, dims=([0], [0]))
+    assert got.shape == (3,)
+    assert torch.allclose(got, want, rtol=1e-13, atol=0)
+    c = us.create_standard(13)
+    area = us.integrate(c, lambda s: torch.ones((2,) * 12 + (4,), device=DEV, dtype=torch.float64), False, 2, xp=torch, device=DEV, dtype=torch.float64)
+    assert abs(area.item() - c.surface_area()) <= 0.2 * c.surface_area()  # n = 2 is a crude rule; the point is that it runs
+
+
+def test_result_dtypes_follow_the_reference_promotion():
+    """integrate(dtype=float32) stays float32 also when f is constant along an axis (the summed
+    weight keeps the rule's dtype), and the separable branch returns each axis in promote(value,
+    weight) even when other axes are wider (reference: vecdot per axis, _integral.py:245-276)."""
+    c = us.create_spherical()
+    one = us.integrate(c, lambda s: torch.ones((1, 1), device=DEV, dtype=torch.float32), False, 6, xp=torch, device=DEV, dtype=torch.float32)
+    assert one.dtype == torch.float32 and abs(one.item() - 4 * math.pi) < 1e-5
+    sep = us.integrate(c, lambda s: {k: torch.ones_like(v) for k, v in s.items()}, True, 6, xp=torch, device=DEV, dtype=None)
+    xs, ws = us.roots(c, 6, expand_dims_x=False, xp=torch, device=DEV, dtype=None)
+    for node in c.s_nodes:
+        assert sep[node].dtype == torch.promote_types(xs[node].dtype, ws[node].dtype), node

@@ -605,3 +605,61 @@ def test_jacobian_standard_tree_and_broadcast():
     assert J.shape == (n + 1, n + 1, 2 * n + 1)
     area = torch.trapezoid(torch.trapezoid(torch.trapezoid(J, ax["theta2"].ravel(), dim=2), ax["theta1"].ravel(), dim=1), ax["theta0"].ravel(), dim=0)
     assert abs(area.item() - c.surface_area()) < 2e-2
+
+
+def test_row_matrix_entry_points_and_plan_seal():
+    """us_from_cartesian_rows / us_to_cartesian_rows (base pointer + row pitch) give the bits of the
+    pointer-table entry points, and every entry point refuses a plan whose seal does not match
+    (a hand-built or modified us_plan_t must not reach the kernels)."""
+    import ctypes as C
+
+    from ultrasphere_b200 import _native
+    from ultrasphere_b200._plan import plan_for
+
+    lib = _native.lib()
+    c = us.create_hopf(3)
+    ct = plan_for(c)
+    n = 300_000
+    x = torch.rand((c.c_ndim, n), device=DEV, dtype=torch.float64) * 2 - 1
+    want = c.from_cartesian({k: x[i].clone() for i, k in enumerate(c.c_nodes)})  # mapping input: pointer tables
+    out = torch.empty((c.s_ndim + 1, n), device=DEV, dtype=torch.float64)
+    stream = torch.cuda.current_stream().cuda_stream
+    assert lib.us_from_cartesian_rows(ct.plan_ref, _native.US_F64, n, x.data_ptr(), n * 8, out.data_ptr(), n * 8, stream) == 0
+    assert torch.equal(out[0], want["r"])
+    for s, node in enumerate(c.s_nodes):
+        assert torch.equal(out[1 + s], want[node]), node
+    back = torch.empty_like(x)
+    ang = (C.c_void_p * c.s_ndim)(*[out[1 + s].data_ptr() for s in range(c.s_ndim)])
+    assert lib.us_to_cartesian_rows(ct.plan_ref, _native.US_F64, n, ang, out[0].data_ptr(), back.data_ptr(), n * 8, stream) == 0
+    assert torch.equal(back, c.to_cartesian(want, as_array=True))
+    forged = _native.UsPlan.from_buffer_copy(ct.plan)
+    forged.node[0] ^= 1 << 24  # another leaf slot: still plausible counts, different program
+    rc = lib.us_from_cartesian_rows(C.byref(forged), _native.US_F64, n, x.data_ptr(), n * 8, out.data_ptr(), n * 8, stream)
+    assert rc == -3 and b"us_plan_compile" in lib.us_last_error_string()
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("spec,tdt", [("standard:9", torch.float32), ("hopf:3", torch.float64), ("spherical", torch.float64)])
+def test_pool_geometry_does_not_change_the_bits(spec, tdt):
+    """us_set_tuning only moves work between consumer groups and buffers: whatever the cut of the
+    shared-memory pool (and with the ragged last tile riding in the same launch), the results are
+    bit-identical."""
+    from ultrasphere_b200 import _native
+
+    lib = _native.lib()
+    c = make(us, spec)
+    n = (1 << 21) + 1284  # ragged: the last tile is partial, a multiple of 16 bytes
+    x = torch.rand((c.c_ndim, n), device=DEV, dtype=tdt) * 2 - 1
+    ref_s = c.from_cartesian(x)
+    ref_x = c.to_cartesian(ref_s, as_array=True)
+    try:
+        for groups, bufs in ((1, 2), (2, 3), (3, 7), (5, 6)):
+            assert lib.us_set_tuning(b"tile_groups", groups) == 0 and lib.us_set_tuning(b"tile_bufs", bufs) == 0
+            s = c.from_cartesian(x)
+            for k in ref_s:
+                assert torch.equal(s[k], ref_s[k]), (groups, bufs, k)
+            assert torch.equal(c.to_cartesian(s, as_array=True), ref_x), (groups, bufs)
+        assert lib.us_set_tuning(b"no_such_knob", 1) == -1
+    finally:
+        lib.us_set_tuning(b"tile_groups", 0)
+        lib.us_set_tuning(b"tile_bufs", 0)

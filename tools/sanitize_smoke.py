@@ -10,7 +10,7 @@ dev = "cuda:0"
 for spec in ("standard:9", "hopf:3", "random:32:0", "spherical"):
     c = make(us, spec)
     for dt in (torch.float32, torch.float64):
-        for n in (1000, 303_104 + 777):  # strided only; tiled (>= 296 tiles) + ragged tail
+        for n in (1000, 1_212_416 + 772, 700_001):  # strided only; tile / ring kernels with a ragged last tile; unaligned (strided throughout)
             x = torch.rand((c.c_ndim, n), device=dev, dtype=dt) * 2 - 1
             s = c.from_cartesian(x)
             y = c.to_cartesian(s, as_array=True)

@@ -138,6 +138,21 @@ def volume(c_ndim: int, /, r: float = 1) -> float:
     return math.pi ** (c_ndim / 2) / math.exp(math.lgamma(c_ndim / 2.0 + 1.0)) * r**c_ndim
 
 
+_transform_module: Any = None
+
+
+def _transform() -> Any:
+    """The kernel-launching half of the package, imported on first use (it loads torch and the
+    shared library) and remembered: an ``import`` statement per call costs about a microsecond,
+    a tenth of what a small transform takes end to end."""
+    global _transform_module
+    if _transform_module is None:
+        from . import _transform as module
+
+        _transform_module = module
+    return _transform_module
+
+
 class SphericalCoordinates[TSpherical, TCartesian]:
     """Polyspherical coordinates described by a rooted cos/sin tree.
 
@@ -241,9 +256,7 @@ class SphericalCoordinates[TSpherical, TCartesian]:
 
         One fused kernel launch (``us_from_cartesian``); see ``_transform.from_cartesian``.
         """
-        from ._transform import from_cartesian
-
-        return from_cartesian(self, cartesian)
+        return _transform().from_cartesian(self, cartesian)
 
     def to_cartesian(self, spherical: Mapping[Any, Any], /, *, as_array: bool = False) -> Any:
         """Spherical → Cartesian.  ``spherical`` maps every angle (and optionally ``"r"``) to a
@@ -251,9 +264,7 @@ class SphericalCoordinates[TSpherical, TCartesian]:
 
         One fused kernel launch (``us_to_cartesian``); see ``_transform.to_cartesian``.
         """
-        from ._transform import to_cartesian
-
-        return to_cartesian(self, spherical, as_array=as_array)
+        return _transform().to_cartesian(self, spherical, as_array=as_array)
 
     def to_cartesian_dot(self, spherical: Mapping[Any, Any], k: Any, /) -> Any:
         """``sum_v k[v] * x_v`` for ``x = to_cartesian(spherical, as_array=True)`` — the reference

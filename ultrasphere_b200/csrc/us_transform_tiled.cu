@@ -68,7 +68,7 @@ static_assert((kGroupSlots & (kGroupSlots - 1)) == 0, "slot count is a power of 
 // would only serialise them again).
 template <typename T>
 __device__ __forceinline__ void producer_loop(const TileParams& p, unsigned char* bufs, uint32_t buf_bytes, int n_groups, int n_bufs,
-                                              int64_t n_tiles, PoolShared* sh) {
+                                              int64_t n_tiles, int tail_points, PoolShared* sh) {
   constexpr int P = kGroupThreads * (16 / (int)sizeof(T));
   const bool leader = elect_one();
   const uint64_t policy = policy_evict_first();
@@ -84,12 +84,14 @@ __device__ __forceinline__ void producer_loop(const TileParams& p, unsigned char
     }
     unsigned char* dst = bufs + (size_t)b * buf_bytes;
     uint64_t* bar = &sh->full[g][slot];
-    if (leader) mbar_arrive_expect_tx(bar, (uint32_t)n_rows * (uint32_t)kRowBytes);
+    // the ragged last tile (tail_points > 0) copies only the bytes that exist: a multiple of 16
+    const uint32_t row_bytes = (tail_points > 0 && tile == n_tiles - 1) ? (uint32_t)tail_points * (uint32_t)sizeof(T) : (uint32_t)kRowBytes;
+    if (leader) mbar_arrive_expect_tx(bar, (uint32_t)n_rows * row_bytes);
     const int64_t first = tile * P;
 #pragma unroll 4
     for (int row = 0; row < n_rows; ++row) {
       const T* src = (const T*)p.in[row] + first;
-      if (leader) tma_load_row(dst + (size_t)row * kRowBytes, src, (uint32_t)kRowBytes, bar, policy);
+      if (leader) tma_load_row(dst + (size_t)row * kRowBytes, src, row_bytes, bar, policy);
     }
     if (++b == n_bufs) {
       b = 0;
@@ -151,7 +153,7 @@ __device__ __forceinline__ PoolShared* pool_init(unsigned char* smem_raw, int n_
 // =================================================================================================
 template <typename T, int V>
 __global__ void __launch_bounds__(32 + kGroupThreads * max_groups<T>(), 1)
-    to_cartesian_tiled(const __grid_constant__ TileParams p, int64_t n_tiles, int n_groups, int n_bufs) {
+    to_cartesian_tiled(const __grid_constant__ TileParams p, int64_t n_tiles, int n_groups, int n_bufs, int tail_points) {
   constexpr int P = kGroupThreads * V;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   PoolShared* sh = pool_init(smem_raw, n_groups, n_bufs);
@@ -161,7 +163,7 @@ __global__ void __launch_bounds__(32 + kGroupThreads * max_groups<T>(), 1)
   const int tid = threadIdx.x;
   const int warp = warp_index_uniform();
   if (warp == 0) {
-    producer_loop<T>(p, bufs, buf_bytes, n_groups, n_bufs, n_tiles, sh);
+    producer_loop<T>(p, bufs, buf_bytes, n_groups, n_bufs, n_tiles, tail_points, sh);
     return;
   }
   const int t = (tid - 32) & (kGroupThreads - 1);
@@ -171,6 +173,9 @@ __global__ void __launch_bounds__(32 + kGroupThreads * max_groups<T>(), 1)
     unsigned char* mine = bufs + (size_t)at.b * buf_bytes + t * 16;
     mbar_wait(&sh->full[group][at.slot], at.parity);
     const int64_t g = at.tile * P + (int64_t)t * V;
+    // in the ragged last tile a thread either owns V whole points or none (the tail is a multiple of 16 bytes)
+    const bool live = tail_points == 0 || at.tile != n_tiles - 1 || t * V < tail_points;
+    if (live) {
     Vec<T, V> cur;
     if (has_r) {
       cur = lds_at<T, V>(mine, (uint32_t)nn * kRowBytes);
@@ -202,6 +207,7 @@ __global__ void __launch_bounds__(32 + kGroupThreads * max_groups<T>(), 1)
       if (oc) stg_vec<T, V>(oc + g, pc);
       if (os) stg_vec<T, V>(os + g, ps);
       th = th_next;
+    }
     }
     if (p.max_park) fence_proxy_async();
     __syncwarp();
@@ -250,7 +256,7 @@ __device__ __noinline__ void chain_redo(const TileParams& p, const unsigned char
 // logic of the operand that is known to be a norm.
 template <typename T, int V, int CHAIN>
 __global__ void __launch_bounds__(32 + kGroupThreads * max_groups<T>(), 1)
-    from_cartesian_tiled(const __grid_constant__ TileParams p, int64_t n_tiles, int n_groups, int n_bufs) {
+    from_cartesian_tiled(const __grid_constant__ TileParams p, int64_t n_tiles, int n_groups, int n_bufs, int tail_points) {
   constexpr int P = kGroupThreads * V;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   PoolShared* sh = pool_init(smem_raw, n_groups, n_bufs);
@@ -261,7 +267,7 @@ __global__ void __launch_bounds__(32 + kGroupThreads * max_groups<T>(), 1)
   const int tid = threadIdx.x;
   const int warp = warp_index_uniform();
   if (warp == 0) {
-    producer_loop<T>(p, bufs, buf_bytes, n_groups, n_bufs, n_tiles, sh);
+    producer_loop<T>(p, bufs, buf_bytes, n_groups, n_bufs, n_tiles, tail_points, sh);
     return;
   }
   const int t = (tid - 32) & (kGroupThreads - 1);
@@ -271,6 +277,8 @@ __global__ void __launch_bounds__(32 + kGroupThreads * max_groups<T>(), 1)
     unsigned char* mine = bufs + (size_t)at.b * buf_bytes + t * 16;
     mbar_wait(&sh->full[group][at.slot], at.parity);
     const int64_t g = at.tile * P + (int64_t)t * V;
+    const bool live = tail_points == 0 || at.tile != n_tiles - 1 || t * V < tail_points;  // see to_cartesian_tiled
+    if (live) {
     if (r_out) {
       // leaves in c_nodes order, sequential, each square and each add rounded once
       Vec<T, V> acc;
@@ -348,8 +356,9 @@ __global__ void __launch_bounds__(32 + kGroupThreads * max_groups<T>(), 1)
         T* o = (T*)d.out_a;
         if (o) stg_vec<T, V>(o + g, th);
       }
-      if (p.max_park) fence_proxy_async();
     }
+    }
+    if (p.max_park) fence_proxy_async();
     __syncwarp();
     if ((tid & 31) == 0) mbar_arrive(&sh->empty[at.b]);
   }
@@ -482,6 +491,7 @@ static int try_tiled(const XformParams& p, int dtype, cudaStream_t st) {
   if (!TO && p.r_out && !aligned16(p.r_out)) return kNotTaken;
   int P = kGroupThreads * (16 / esz);
   int64_t n_tiles = p.n / P;
+  int64_t done = 0;
   int n_groups = 0, n_bufs = 0;
   if (!pool_geometry(n_rows, dtype == US_F32 ? max_groups<float>() : max_groups<double>(), &n_groups, &n_bufs)) {
     // wide tree: the rows stream through a ring instead of whole tiles being resident
@@ -489,10 +499,15 @@ static int try_tiled(const XformParams& p, int dtype, cudaStream_t st) {
     if (p.n / ring_p < 2 * sm_count()) return kNotTaken;
     const int rc = launch_ring<TO>(p, dtype, st, &P);
     if (rc != 0) return rc;
-    n_tiles = p.n / P;
+    done = (p.n / P) * P;
   } else {
     // small batches: below a few tiles per group the pipeline's fill/drain costs more than it hides
     if (n_tiles < (int64_t)tuning().min_tiles * sm_count()) return kNotTaken;
+    // a ragged end whose rows are a multiple of 16 bytes (always the case when the operands are rows
+    // of one matrix) rides in the same launch as a partial last tile; otherwise the strided kernel below
+    const int64_t rest = p.n - n_tiles * P;
+    const int tail_points = (rest > 0 && (rest * esz) % 16 == 0) ? (int)rest : 0;
+    if (tail_points) ++n_tiles;
     const void* fn = dtype == US_F32 ? variant<float>(TO, chain_kind(p.plan)) : variant<double>(TO, chain_kind(p.plan));
     const size_t smem = (size_t)kPoolHeader + (size_t)n_bufs * n_rows * kRowBytes;
     const int threads = 32 + kGroupThreads * n_groups;
@@ -504,11 +519,12 @@ static int try_tiled(const XformParams& p, int dtype, cudaStream_t st) {
     TileParams body;
     if (!build_walk<kTileCap>(p, TO, (uint32_t)kRowBytes, 0u, body)) return kNotTaken;
     int64_t tiles = n_tiles;
-    void* args[] = {(void*)&body, (void*)&tiles, (void*)&n_groups, (void*)&n_bufs};
+    int tail = tail_points;
+    void* args[] = {(void*)&body, (void*)&tiles, (void*)&n_groups, (void*)&n_bufs, (void*)&tail};
     US_CUDA_TRY(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3((unsigned)threads), args, smem, st), "tiled launch");
+    done = tail_points ? p.n : n_tiles * P;
   }
-  // ragged tail (< one tile): the strided kernel on the remaining points
-  const int64_t done = n_tiles * P;
+  // ragged tail (< one tile) that could not ride along: the strided kernel on the remaining points
   const int64_t rest = p.n - done;
   if (rest > 0) {
     XformParams tail = p;
