@@ -674,6 +674,30 @@ def run_b200(args: argparse.Namespace, emit) -> None:
                 quadrature[name] = {"error": f"integral off by {rel} relative: not reported", "rel_err_vs_analytic": rel}
                 continue
             quadrature[name] = {"ms_per_integral": ms, "nodes_per_s": nodes / (ms * 1e-3), "rel_err_vs_analytic": rel}
+        # the fused form once more, captured in ONE CUDA graph (f's kernels, the contraction and the
+        # NCCL all-reduce of the sharded partial sums): what is left is device time
+        try:
+            captured = us.IntegralGraph(c4, forms["fused_functional"], False, nq, xp=torch, device=dev, dtype=torch.float64, group=group)
+            for _ in range(3):
+                got = captured()
+            barrier()
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 20
+            q0.record()
+            for _ in range(reps):
+                got = captured()
+            q1.record()
+            barrier()
+            ms = max_over_ranks([q0.elapsed_time(q1) / reps])[0]
+            rel = abs(got.item() - want) / want
+            if rel <= 1e-12:
+                quadrature["fused_functional_graph"] = {"ms_per_integral": ms, "nodes_per_s": nodes / (ms * 1e-3), "rel_err_vs_analytic": rel,
+                                                        "how": "us.IntegralGraph: the whole sharded integral, all-reduce included, replayed as one CUDA graph"}
+            else:
+                quadrature["fused_functional_graph"] = {"error": f"integral off by {rel} relative: not reported", "rel_err_vs_analytic": rel}
+            del captured
+        except Exception as exc:  # a box whose NCCL cannot be captured: the eager legs above stand
+            quadrature["fused_functional_graph"] = {"error": f"{type(exc).__name__}: {exc}"}
         if world > 1:
             # the check of tests/test_gpu_multi.py under THIS run's ranks: every sharded integral
             # (two trees, both integrand forms, slabbed) against the same integral unsharded

@@ -382,3 +382,17 @@ def test_result_dtypes_follow_the_reference_promotion():
     xs, ws = us.roots(c, 6, expand_dims_x=False, xp=torch, device=DEV, dtype=None)
     for node in c.s_nodes:
         assert sep[node].dtype == torch.promote_types(xs[node].dtype, ws[node].dtype), node
+
+
+def test_integral_graph_replays_with_updated_parameters():
+    """us.IntegralGraph: the integral captured once, replayed after in-place parameter updates;
+    every replay equals the eager integrate() of the same parameters."""
+    c = us.create_standard(4)
+    k = torch.tensor([0.3, -0.2, 0.5, 0.1, 0.7], device=DEV, dtype=torch.float64)
+    f = lambda s: torch.exp(c.to_cartesian_dot(s, k))  # noqa: E731
+    g = us.IntegralGraph(c, f, False, 12, xp=torch, device=DEV, dtype=torch.float64)
+    for scale in (1.0, 0.5, 2.0):
+        k.copy_(torch.tensor([0.3, -0.2, 0.5, 0.1, 0.7], device=DEV, dtype=torch.float64) * scale)
+        got = g().clone()
+        want = us.integrate(c, f, False, 12, xp=torch, device=DEV, dtype=torch.float64)
+        assert torch.equal(got, want), scale

@@ -19,6 +19,7 @@ create_hopf, create_random = _cr.create_hopf, _cr.create_random
 create_from_branching_types = _cr.create_from_branching_types
 # quadrature, sampling, fused reductions
 roots, integrate = _in.roots, _in.integrate
+IntegralGraph = _in.IntegralGraph  # an extension: integrate() captured in a CUDA graph, NCCL all-reduce included
 rule_backend, set_rule_backend = _in.rule_backend, _in.set_rule_backend
 weighted_reduce, separable_reduce = _in.weighted_reduce, _in.separable_reduce
 random_ball = _ra.random_ball

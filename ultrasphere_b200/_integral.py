@@ -587,6 +587,67 @@ def integrate(
     return _finish(out, group, sharded=sharded)
 
 
+class IntegralGraph:
+    """``integrate(...)`` captured ONCE in a CUDA graph and replayed: the kernels ``f`` launches, the
+    fused contraction and — for an integral sharded over ``group`` — the NCCL all-reduce of the
+    partial sums all become one graph launch.
+
+    What it is for: an integral that is evaluated again and again (a parameter sweep, an
+    iteration) costs ``integrate`` a dozen launches and their host work per call, which at 8 GPUs
+    (21 M nodes per rank of BASELINE's C5 grid) is more than the kernels themselves take.  ``f``
+    must be capturable (device tensors in, no host synchronisation) and must read whatever
+    changes between evaluations from tensors that are updated IN PLACE::
+
+        k = torch.tensor([...], device="cuda", dtype=torch.float64)
+        g = us.IntegralGraph(c, lambda s: torch.exp(c.to_cartesian_dot(s, k)), False, 96, xp=torch,
+                             dtype=torch.float64, group=pg)
+        for new_k in sweep:
+            k.copy_(new_k)
+            value = g()          # the graph's output buffer: valid until the next replay
+
+    Same arguments and result as :func:`integrate` (dense or separable).  Every rank of ``group``
+    must construct and replay the object alike — a replay is a collective call.
+    """
+
+    def __init__(
+        self,
+        c: SphericalCoordinates[Any, Any],
+        f: Callable[[Mapping[Any, torch.Tensor]], Any] | Mapping[Any, torch.Tensor] | torch.Tensor,
+        does_f_support_separation_of_variables: bool,
+        n: int,
+        *,
+        xp: Any,
+        device: Any | None = None,
+        dtype: Any | None = None,
+        slab_bytes: int | None = None,
+        group: Any | None = None,
+        warmup: int = 2,
+    ) -> None:
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
+        run = lambda: integrate(  # noqa: E731
+            c, f, does_f_support_separation_of_variables, n, xp=xp, device=self.device, dtype=dtype, slab_bytes=slab_bytes, group=group
+        )
+        with torch.cuda.device(self.device), torch.no_grad():
+            # eager passes on a side stream first: rule tables, plan, scratch and NCCL's own buffers
+            # must exist before the capture begins
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                for _ in range(max(1, warmup)):
+                    run()
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.result = run()
+
+    def __call__(self) -> Any:
+        self.graph.replay()
+        return self.result
+
+
 def shard_rows(n_rows: int, rank: int, world: int) -> tuple[int, int]:
     """Contiguous share ``[lo, hi)`` of the leading grid axis owned by ``rank`` (may be empty)."""
     return (n_rows * rank) // world, (n_rows * (rank + 1)) // world

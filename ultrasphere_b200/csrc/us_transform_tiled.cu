@@ -247,10 +247,35 @@ __device__ __noinline__ void chain_redo(const TileParams& p, const unsigned char
   }
 }
 
+// create_hopf(q): the perfect binary tree — `c` nodes over `a` nodes, 2^q leaves.  Its walk is
+// known at compile time, so it is spelled as a recursion over the program position instead of being
+// interpreted: the subtree at position I spans 2^Q - 1 nodes, its cos child sits at I + 1 and its
+// sin child at I + 2^(Q-1); descriptors become constant-bank operands at fixed offsets, the
+// partial norms stay in registers (no parking, no kind switch, no moves at the switch's merge
+// point), and the two sub-evaluations are independent chains the scheduler can interleave.
+template <typename T, int V, int Q, int I>
+__device__ __forceinline__ Vec<T, V> hopf_norm(const TileParams& p, const unsigned char* mine, int64_t g) {
+  const NodeDesc& d = p.d[I];
+  Vec<T, V> th, nrm;
+  if constexpr (Q == 1) {  // `a`: two leaves
+    const Vec<T, V> vc = lds_at<T, V>(mine, d.row_a);
+    const Vec<T, V> vs = lds_at<T, V>(mine, d.row_b);
+    node_from_vec<V, false, false>(vs.v, vc.v, th.v, nrm.v);
+  } else {  // `c`: two subtree norms (>= 0)
+    const Vec<T, V> nc = hopf_norm<T, V, Q - 1, I + 1>(p, mine, g);
+    const Vec<T, V> ns = hopf_norm<T, V, Q - 1, I + (1 << (Q - 1))>(p, mine, g);
+    node_from_vec<V, true, true>(ns.v, nc.v, th.v, nrm.v);
+  }
+  T* o = (T*)d.out_a;
+  if (o) stg_vec<T, V>(o + g, th);
+  return nrm;
+}
+
 // =================================================================================================
 // from_cartesian
 // =================================================================================================
-// CHAIN: 0 = any tree (node kinds decoded per node); 1 = `b...ba` (create_standard), 2 = `b'...b'a`
+// CHAIN (the tree's shape class): 3 / 4 = create_hopf(2) / create_hopf(3), evaluated by hopf_norm;
+// 0 = any tree (node kinds decoded per node); 1 = `b...ba` (create_standard), 2 = `b'...b'a`
 // (create_standard_prime): every node but the last has one leaf operand and the running norm as the
 // other, so the walk needs no kind switch, no operand selection, and the atan2 can skip the sign
 // logic of the operand that is known to be a norm.
@@ -290,7 +315,9 @@ __global__ void __launch_bounds__(32 + kGroupThreads * max_groups<T>(), 1)
       stg_vec<T, V>(r_out + g, acc);
     }
     Vec<T, V> cur;
-    if constexpr (CHAIN != 0) {
+    if constexpr (CHAIN >= 3) {
+      cur = hopf_norm<T, V, CHAIN - 1, 0>(p, mine, g);
+    } else if constexpr (CHAIN != 0) {
       // fast paths unchecked; one range test per point at the end (us_common.cuh: chain_in_range)
       Vec<T, V> in_s, in_c;
       {
@@ -375,12 +402,27 @@ static const void* variant(bool to, int chain) {
   if (to) return (const void*)&to_cartesian_tiled<T, V>;
   if (chain == 1) return (const void*)&from_cartesian_tiled<T, V, 1>;
   if (chain == 2) return (const void*)&from_cartesian_tiled<T, V, 2>;
+  // the compile-time hopf walk pays where the kernel is bound by instruction issue (float64: +12 %,
+  // tools/ab_inproc.py); the float32 kernel sits on HBM and is faster interpreted (fewer registers)
+  if constexpr (sizeof(T) == 8) {
+    if (chain == 3) return (const void*)&from_cartesian_tiled<T, V, 3>;
+    if (chain == 4) return (const void*)&from_cartesian_tiled<T, V, 4>;
+  }
   return (const void*)&from_cartesian_tiled<T, V, 0>;
 }
 
-// 1: every node but the last is `b` and the last is `a`; 2: same with `b'`; 0: anything else
+// does the program at [i, i + 2^q - 1) spell create_hopf(q): `c` over two copies of create_hopf(q-1), `a` at the bottom?
+static bool is_hopf(const us_plan_t& plan, int i, int q) {
+  if (q == 1) return node_kind(plan.node[i]) == US_NODE_A;
+  return node_kind(plan.node[i]) == US_NODE_C && is_hopf(plan, i + 1, q - 1) && is_hopf(plan, i + (1 << (q - 1)), q - 1);
+}
+
+// shape class of the tree: 1: every node but the last is `b` and the last is `a`; 2: same with `b'`;
+// 3 / 4: create_hopf(2) / create_hopf(3); 0: anything else
 static int chain_kind(const us_plan_t& plan) {
   const int nn = plan.n_nodes;
+  if (nn == 3 && is_hopf(plan, 0, 2)) return 3;
+  if (nn == 7 && is_hopf(plan, 0, 3)) return 4;
   if (nn < 2 || plan.max_stack != 0 || node_kind(plan.node[nn - 1]) != US_NODE_A) return 0;
   const int first = node_kind(plan.node[0]);
   if (first != US_NODE_B && first != US_NODE_BP) return 0;
