@@ -663,3 +663,57 @@ def test_pool_geometry_does_not_change_the_bits(spec, tdt):
     finally:
         lib.us_set_tuning(b"tile_groups", 0)
         lib.us_set_tuning(b"tile_bufs", 0)
+
+
+def test_parity_report():
+    """The measured error distribution behind the parity claim, per BASELINE config and dtype, on
+    2^20 seeded points each: max and 99.99th-percentile distance from the NumPy oracle for r, the
+    angles (ulp of the angle) and the leaves (ulp element-wise and in ulp(r)), float32 also as a
+    relative error.  Written to gpurun_out/parity_report.json (copied to profiles/ by the builder);
+    the assertions are the north star's bars."""
+    import json
+    import os
+
+    n = 1 << 20
+    report = {"points_per_config": n, "oracle": "oracle/vks_oracle.py (NumPy), inputs default_rng(0).uniform(-1, 1)", "configs": {}}
+    for spec in ("spherical", "standard:9", "hopf:3", "standard_prime:8", "random:32:0"):
+        c, t = make(us, spec), vo.make(spec)
+        depth = depth_of(c)
+        for dname, ndt, tdt in DTYPES:
+            x = np.random.default_rng(0).uniform(-1, 1, (c.c_ndim, n)).astype(ndt)
+            want = vo.from_cartesian(t, x)
+            got = c.from_cartesian(dev(x))
+            eps = np.finfo(ndt).eps
+            d_r = vo.ulp_distance(host(got["r"]), want["r"])
+            ang_g = np.stack([host(got[k]) for k in c.s_nodes])
+            ang_w = np.stack([want[k] for k in c.s_nodes])
+            d_a = vo.ulp_distance(ang_g, ang_w)
+            back = host(c.to_cartesian({k: dev(v) for k, v in want.items()}, as_array=True))
+            wantx = vo.to_cartesian(t, want, as_array=True)
+            d_x = vo.ulp_distance(back, wantx)
+            x_over_r = np.abs(back.astype(np.float64) - wantx.astype(np.float64)) / np.spacing(np.abs(want["r"]).astype(np.float64)).astype(np.float64)[None]
+            rt = host(c.to_cartesian(got, as_array=True))
+            entry = {
+                "r_max_ulp": float(d_r.max()),
+                "angle_max_ulp": float(d_a.max()), "angle_p9999_ulp": float(np.quantile(d_a, 0.9999)),
+                "leaf_max_ulp": float(d_x.max()), "leaf_p9999_ulp": float(np.quantile(d_x, 0.9999)), "leaf_frac_over_4ulp": float((d_x > 4).mean()),
+                "leaf_max_err_in_ulp_of_r": float(x_over_r.max()),
+                "max_leaf_depth": int(depth.max()),
+                "round_trip_max_abs_over_r_eps": float(np.max(np.abs(rt.astype(np.float64) - x) / want["r"].astype(np.float64)[None]) / eps),
+            }
+            if ndt == np.float32:
+                with np.errstate(all="ignore"):
+                    entry["angle_max_rel"] = float(np.nanmax(np.abs(ang_g.astype(np.float64) - ang_w) / np.abs(ang_w.astype(np.float64))))
+                    rel = np.abs(back.astype(np.float64) - wantx) / np.abs(wantx.astype(np.float64))
+                    entry["leaf_max_rel"] = float(np.nanmax(np.where(np.isfinite(rel), rel, 0)))
+            report["configs"][f"{spec}|{dname}"] = entry
+            assert entry["r_max_ulp"] == 0, (spec, dname)
+            if ndt == np.float64:
+                assert entry["angle_max_ulp"] <= F64_ULP and entry["leaf_max_err_in_ulp_of_r"] <= F64_ULP, (spec, entry)
+                assert entry["leaf_max_ulp"] <= F64_ULP + depth.max(), (spec, entry)
+            else:
+                assert entry["angle_max_rel"] <= F32_REL, (spec, entry)
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out_dir, exist_ok=True)
+    with open(os.path.join(out_dir, "parity_report.json"), "w") as fh:
+        json.dump(report, fh, indent=1)

@@ -48,6 +48,7 @@ struct RingConsumer {
       : mine(smem_u32(rows) + (uint32_t)tid * 16u), full(smem_u32(&sh->full[0])), empty(smem_u32(&sh->empty[0])),
         slot(0u), parity(0u), n_slots((uint32_t)slots), lane0((tid & 31) == 0) {}
   __device__ __forceinline__ Vec<T, V> get(uint32_t& used) {
+    US_ASSERT(slot < n_slots && n_slots <= (uint32_t)kMaxRing);
     used = slot;
     mbar_wait_s(full + slot * 8u, parity);
     const Vec<T, V> x = lds_vec_s<T, V>(mine + slot * (uint32_t)kRingRowBytes);
@@ -105,6 +106,7 @@ __device__ __forceinline__ RingShared* ring_init(unsigned char* smem_raw, int n_
 // the parking rows: thread-private columns, plain shared-memory accesses
 template <typename T, int V>
 __device__ __forceinline__ void park_store(uint32_t addr, const Vec<T, V>& x) {
+  US_ASSERT(addr % 16u == 0u);
   uint32_t w[4];
   memcpy(w, &x, 16);
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
@@ -159,6 +161,7 @@ __global__ void __launch_bounds__(kRingBlock, 3) to_cartesian_ring(const __grid_
       mul_vec<V>(cur.v, cs.v, pc.v);
       mul_vec<V>(cur.v, sn.v, ps.v);
       const uint32_t kind = d.kind;
+      US_ASSERT(((kind & kNodeKindMask) != US_NODE_C && !(kind & kNodeLinked)) || d.park < (uint32_t)p.max_park * (uint32_t)kRingRowBytes);
       if ((kind & kNodeKindMask) == US_NODE_C) park_store<T, V>(park + d.park, ps);
 #pragma unroll
       for (int v = 0; v < V; ++v) cur.v[v] = ((kind & kNodeKindMask) == US_NODE_B) ? ps.v[v] : pc.v[v];
@@ -226,6 +229,7 @@ __global__ void __launch_bounds__(kRingBlock, 3) from_cartesian_ring(const __gri
       Vec<T, V> th, nxt;
       switch (kind & kNodeKindMask) {  // one specialised body per node kind (see from_cartesian_tiled)
         case US_NODE_A: {
+          US_ASSERT(!(kind & kNodeLinked) || d.park < (uint32_t)p.max_park * (uint32_t)kRingRowBytes);
           if (kind & kNodeLinked) park_store<T, V>(park + d.park, cur);
           uint32_t slot_c, slot_s;
           const Vec<T, V> vc = ring.get(slot_c);
@@ -250,6 +254,7 @@ __global__ void __launch_bounds__(kRingBlock, 3) from_cartesian_ring(const __gri
           break;
         }
         default: {
+          US_ASSERT(d.park < (uint32_t)p.max_park * (uint32_t)kRingRowBytes);
           const Vec<T, V> vs = lds_vec_s<T, V>(park + d.park);
           node_from_vec<V, true, true>(vs.v, cur.v, th.v, nxt.v);
           break;

@@ -110,10 +110,12 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 
 template <typename T, int V>
 __device__ __forceinline__ Vec<T, V> lds_at(const unsigned char* mine, uint32_t row_off) {
+  US_ASSERT(row_off % kRowBytes == 0 && row_off < (kTileCap + 1) * kRowBytes);  // a whole row of this thread's tile
   return *reinterpret_cast<const Vec<T, V>*>(mine + row_off);
 }
 template <typename T, int V>
 __device__ __forceinline__ void sts_at(unsigned char* mine, uint32_t row_off, const Vec<T, V>& x) {
+  US_ASSERT(row_off % kRowBytes == 0 && row_off < (kTileCap + 1) * kRowBytes);
   *reinterpret_cast<Vec<T, V>*>(mine + row_off) = x;
 }
 
@@ -171,6 +173,8 @@ __global__ void __launch_bounds__(32 + kGroupThreads * max_groups<T>(), 1)
   const int group = (warp - 1) / kGroupWarps;
   for (TileCursor at(group); at.tile < n_tiles; at.next(n_groups, n_bufs)) {
     unsigned char* mine = bufs + (size_t)at.b * buf_bytes + t * 16;
+    US_ASSERT(group < n_groups && at.b >= 0 && at.b < n_bufs && at.slot >= 0 && at.slot < kGroupSlots);
+    US_ASSERT(kPoolHeader + (size_t)(at.b + 1) * buf_bytes <= (size_t)kSmemBytes);
     mbar_wait(&sh->full[group][at.slot], at.parity);
     const int64_t g = at.tile * P + (int64_t)t * V;
     // in the ragged last tile a thread either owns V whole points or none (the tail is a multiple of 16 bytes)
@@ -300,6 +304,8 @@ __global__ void __launch_bounds__(32 + kGroupThreads * max_groups<T>(), 1)
   const int group = (warp - 1) / kGroupWarps;
   for (TileCursor at(group); at.tile < n_tiles; at.next(n_groups, n_bufs)) {
     unsigned char* mine = bufs + (size_t)at.b * buf_bytes + t * 16;
+    US_ASSERT(group < n_groups && at.b >= 0 && at.b < n_bufs && at.slot >= 0 && at.slot < kGroupSlots);
+    US_ASSERT(kPoolHeader + (size_t)(at.b + 1) * buf_bytes <= (size_t)kSmemBytes);
     mbar_wait(&sh->full[group][at.slot], at.parity);
     const int64_t g = at.tile * P + (int64_t)t * V;
     const bool live = tail_points == 0 || at.tile != n_tiles - 1 || t * V < tail_points;  // see to_cartesian_tiled
