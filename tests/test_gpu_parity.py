@@ -691,7 +691,7 @@ def test_parity_report():
             back = host(c.to_cartesian({k: dev(v) for k, v in want.items()}, as_array=True))
             wantx = vo.to_cartesian(t, want, as_array=True)
             d_x = vo.ulp_distance(back, wantx)
-            x_over_r = np.abs(back.astype(np.float64) - wantx.astype(np.float64)) / np.spacing(np.abs(want["r"]).astype(np.float64)).astype(np.float64)[None]
+            x_over_r = np.abs(back.astype(np.float64) - wantx.astype(np.float64)) / np.spacing(np.abs(want["r"])).astype(np.float64)[None]  # ulp of r in the data's own type
             rt = host(c.to_cartesian(got, as_array=True))
             entry = {
                 "r_max_ulp": float(d_r.max()),

@@ -84,7 +84,25 @@ def call_to(v):
 
 
 times = {(v, d): [] for v in variants for d in ("from", "to")}
-for direction, fn in (("from", call_from), ("to", call_to)):
+block = int(os.environ.get("AB_BLOCK", "0"))  # > 0: sustained mode — blocks of this many back-to-back calls per variant
+if block:
+    for direction, fn in (("from", call_from), ("to", call_to)):
+        for v in variants:
+            fn(v)
+        torch.cuda.synchronize()
+        for rep in range(reps):
+            order = variants if rep % 2 == 0 else variants[::-1]
+            for v in order:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(block):
+                    fn(v)
+                e1.record()
+                e1.synchronize()
+                times[(v, direction)].append(e0.elapsed_time(e1) / block)
+        if direction == "from":
+            call_from(variants[-1])
+for direction, fn in ((("from", call_from), ("to", call_to)) if not block else ()):
     for v in variants:
         fn(v)
     torch.cuda.synchronize()
@@ -102,7 +120,7 @@ pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
 if os.path.isfile(pk):
     peak = json.load(open(pk))["hbm_gbs"]
 gb = n * 2 * c.c_ndim * esz / 1e9
-print(f"{spec} {dt} n={n} reps={reps} round-trip max err {err:.2e}")
+print(f"{spec} {dt} n={n} reps={reps} {'blocks of ' + str(block) + ' back-to-back calls' if block else 'isolated calls'} round-trip max err {err:.2e}")
 print("| variant | from median ms (frac) | from best | to median ms (frac) | to best |\n|---|---|---|---|---|")
 for v in variants:
     f, t = times[(v, "from")], times[(v, "to")]
