@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 def test_bench_prints_one_contract_line():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     done = subprocess.run(
-        [sys.executable, os.path.join(root, "bench.py"), "--steps", "3", "--warmup", "3", "--points", "8000000", "--no-cpu-baseline"],
+        [sys.executable, os.path.join(root, "bench.py"), "--steps", "3", "--warmup", "3", "--points", "8000000", "--no-cpu-baseline", "--leg-scale", "0.05"],
         capture_output=True, text=True, cwd=root, timeout=900,
     )
     assert done.returncode == 0, done.stderr[-3000:]
@@ -20,7 +20,7 @@ def test_bench_prints_one_contract_line():
     assert len(lines) == 1, lines
     line = json.loads(lines[0])
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
-                "dtype", "data", "config", "roofline", "e2e", "gpu_launches", "clocks", "quadrature"):
+                "dtype", "data", "config", "roofline", "e2e", "gpu_launches", "clocks", "quadrature", "configs"):
         assert key in line, key
     assert line["n_gpus"] == 1 and line["steps"] == 3 and line["gpu_launches"] == 6 and line["dtype"] == "f32"
     roof = line["roofline"]
@@ -32,3 +32,11 @@ def test_bench_prints_one_contract_line():
     quad = line["quadrature"]
     assert quad["reference_form"]["rel_err_vs_analytic"] <= 1e-12 and quad["fused_functional"]["rel_err_vs_analytic"] <= 1e-12
     assert quad["fused_functional"]["nodes_per_s"] > quad["reference_form"]["nodes_per_s"] > 0
+    assert quad["fused_functional_graph"]["rel_err_vs_analytic"] <= 1e-12
+    assert roof["copy_in_this_run"]["sustained_copy_gbs"] > 0 and roof["traffic"] > 0
+    assert e2e["host_link_ceiling"]["d2h_gbs"] > 0 and 0 < e2e["frac_of_link_ceiling"] < 1.2
+    legs = line["configs"]
+    for key in ("C1", "C3_hopf3", "C3_standard_prime8", "C4"):
+        leg = legs[key]
+        assert leg["from_cartesian_ms"] > 0 and leg["to_cartesian_ms"] > 0 and 0 < leg["roofline"]["from_cartesian"]["frac"] < 1.1, key
+    assert legs["C3_hopf3"]["fp64_pipe"]["from_cartesian"]["frac"] > 0 and "graph_replay" in legs["C1"]

@@ -437,7 +437,7 @@ def _to_cartesian_dense(
             return None
     ct = c._plan or plan_for(c)
     n = first.numel()
-    out = torch.empty((ct.n_leaves, *shape), dtype=dtype, device=device)
+    out = first.new_empty((ct.n_leaves, *shape))
     if n:
         ptrs = ct.angle_ptrs  # reused table: filled and consumed under the GIL, before the call returns
         for i, a in enumerate(angles):
@@ -620,7 +620,7 @@ def _from_cartesian_dense(c: SphericalCoordinates[Any, Any], cartesian: Any) -> 
         if code is None:
             return None
         n = x.numel() // ct.n_leaves
-        out = torch.empty((ct.n_nodes + 1, *x.shape[1:]), dtype=dtype, device=device)
+        out = torch.empty_like(x)  # r and s_ndim angles: as many rows as leaves (the cheapest way to allocate them)
         if n:
             row = n * x.element_size()
             if device.index != _current_device():
