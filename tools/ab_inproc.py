@@ -64,6 +64,7 @@ def apply(v):
         for name in ("tile_groups", "tile_bufs"):
             h.us_set_tuning(name.encode(), 0)
         h.us_set_tuning(b"tile_max_rows", 13)
+        h.us_set_tuning(b"ring_ctas", 0)
         if knobs:
             for kv in knobs[0].split(","):
                 k, val = kv.split("=")

@@ -5,7 +5,8 @@
 // has 33 rows).  Here the rows stream through a RING of row slots instead: the producer warp
 // issues one TMA bulk copy per (tile, row) in exactly the order the consumers will need them, each
 // slot has its own full/empty mbarrier pair, and a consumer warp releases a slot as soon as it has
-// used the row.  Shared memory per CTA is (slots + parking rows) * 4 KB whatever the tree width,
+// used the row.  Shared memory per CTA is (slots + parking rows) * 4 KB whatever the tree width (four
+// CTAs per SM for float32, three for float64),
 // threads keep V = 16 B / sizeof(T).  Deferred branches of `c` nodes are parked in shared memory
 // rows indexed by the depth of the deferral (us_walk.cuh): no per-thread stack, no local memory.
 //
@@ -23,7 +24,7 @@
 
 namespace us {
 
-constexpr int kMaxRing = 16;         // row slots at most
+constexpr int kMaxRing = 32;         // row slots at most
 constexpr int kRingConsumers = 256;  // consumer threads = points per tile / V
 constexpr int kRingBlock = kRingConsumers + 32;
 constexpr int kRingRowBytes = kRingConsumers * 16;
@@ -34,7 +35,7 @@ struct RingShared {
   uint64_t full[kMaxRing];
   uint64_t empty[kMaxRing];
 };
-constexpr int kRingHeader = 256;
+constexpr int kRingHeader = 512;
 static_assert(sizeof(RingShared) <= kRingHeader, "barrier block");
 
 // Consumer side, on shared-space addresses computed once per thread: `mine` already points at this
@@ -114,7 +115,7 @@ __device__ __forceinline__ void park_store(uint32_t addr, const Vec<T, V>& x) {
 
 // =================================================================================================
 template <typename T, int V>
-__global__ void __launch_bounds__(kRingBlock, 3) to_cartesian_ring(const __grid_constant__ RingParams p, int64_t n_tiles, int n_slots) {
+__global__ void __launch_bounds__(kRingBlock, sizeof(T) == 4 ? 4 : 3) to_cartesian_ring(const __grid_constant__ RingParams p, int64_t n_tiles, int n_slots) {
   static_assert(sizeof(T) * V == 16, "ring rows are 16 bytes per thread");
   constexpr int P = kRingConsumers * V;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(kRingBlock, 3) to_cartesian_ring(const __grid_
 
 // =================================================================================================
 template <typename T, int V>
-__global__ void __launch_bounds__(kRingBlock, 3) from_cartesian_ring(const __grid_constant__ RingParams p, int64_t n_tiles, int n_slots) {
+__global__ void __launch_bounds__(kRingBlock, sizeof(T) == 4 ? 4 : 3) from_cartesian_ring(const __grid_constant__ RingParams p, int64_t n_tiles, int n_slots) {
   static_assert(sizeof(T) * V == 16, "ring rows are 16 bytes per thread");
   constexpr int P = kRingConsumers * V;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -274,6 +275,8 @@ static const void* ring_fn(int dtype) {
   return TO ? (const void*)&to_cartesian_ring<double, 2> : (const void*)&from_cartesian_ring<double, 2>;
 }
 
+int ring_ctas_per_sm();
+
 template <bool TO>
 int launch_ring(const XformParams& p, int dtype, cudaStream_t st, int* points_per_tile) {
   const int esz = dtype == US_F32 ? 4 : 8;
@@ -281,9 +284,15 @@ int launch_ring(const XformParams& p, int dtype, cudaStream_t st, int* points_pe
   *points_per_tile = P;
   const int64_t n_tiles = p.n / P;
   const void* fn = ring_fn<TO>(dtype);
-  // three CTAs per SM (75 KB each) as long as the parking rows leave at least 8 ring slots
+  // CTAs per SM — four for float32 (<= 56 registers), three for float64; the float32 from_cartesian
+  // is short of warps, not of ring depth: 4 x 8 consumer warps with 8-13 slots each beat 3 x 8
+  // with 16 (3.70 -> 3.53 ms on create_random(32)), and 2 x 8 with 27 slots lose (4.07 ms) — and
+  // row slots: as many as the share of shared memory holds after the parking rows, at least 8
   const int park_rows = p.plan.max_stack;
-  int n_slots = (74 * 1024 - kRingHeader) / kRingRowBytes - park_rows;
+  int ctas = ring_ctas_per_sm();
+  if (ctas <= 0) ctas = dtype == US_F32 ? 4 : 3;
+  if (ctas > (dtype == US_F32 ? 4 : 3)) ctas = dtype == US_F32 ? 4 : 3;
+  int n_slots = ((227 * 1024 / ctas) - 1024 - kRingHeader) / kRingRowBytes - park_rows;
   if (n_slots > kMaxRing) n_slots = kMaxRing;
   if (n_slots < 8) n_slots = 8;
   const size_t smem = (size_t)kRingHeader + (size_t)(n_slots + park_rows) * kRingRowBytes;

@@ -497,6 +497,7 @@ struct Tuning {
   int bufs = env_int("US_TILE_BUFS", 0);            // buffers in the pool (0: as many as fit)
   int max_rows = env_int("US_TILE_MAX_ROWS", 13);   // wider trees take the row-ring kernels
   int min_tiles = env_int("US_TILED_MIN_TILES", 8); // per SM: smaller batches take the strided kernels
+  int ring_ctas = env_int("US_RING_CTAS", 0);       // resident CTAs per SM the ring kernels size their slots for (0: 4 float32 / 3 float64)
 };
 static Tuning& tuning() {
   static Tuning t;
@@ -590,12 +591,15 @@ static int try_tiled(const XformParams& p, int dtype, cudaStream_t st) {
   return 0;
 }
 
+int ring_ctas_per_sm() { return tuning().ring_ctas; }
+
 int set_tile_tuning(const char* name, int value) {
   Tuning& t = tuning();
   if (!strcmp(name, "tile_groups")) t.groups = value;
   else if (!strcmp(name, "tile_bufs")) t.bufs = value;
   else if (!strcmp(name, "tile_max_rows")) t.max_rows = value;
   else if (!strcmp(name, "tiled_min_tiles")) t.min_tiles = value;
+  else if (!strcmp(name, "ring_ctas")) t.ring_ctas = value < 0 ? 0 : (value > 4 ? 4 : value);
   else return fail(US_EINVAL, "us_set_tuning: unknown knob '%s'", name);
   return 0;
 }
