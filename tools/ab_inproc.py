@@ -65,6 +65,7 @@ def apply(v):
             h.us_set_tuning(name.encode(), 0)
         h.us_set_tuning(b"tile_max_rows", 13)
         h.us_set_tuning(b"ring_ctas", 0)
+        h.us_set_tuning(b"ring_u", 0)  # libraries older than the knob answer US_EINVAL: ignored
         if knobs:
             for kv in knobs[0].split(","):
                 k, val = kv.split("=")

@@ -46,6 +46,7 @@ int try_launch_from_cartesian_tiled(const XformParams& p, int dtype, cudaStream_
 // wide trees: row-ring kernels (us_transform_ring.cu); *points_per_tile = points each tile covered
 template <bool TO>
 int launch_ring(const XformParams& p, int dtype, cudaStream_t st, int* points_per_tile);
+int ring_points_per_tile(int dtype);  // with the current tuning
 // cached cudaFuncSetAttribute(max dynamic smem) + occupancy query
 int resident_ctas(const void* fn, size_t smem, int block_threads, int* per_sm);
 int sm_count();  // of the current device, cached

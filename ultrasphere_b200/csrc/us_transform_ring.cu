@@ -5,10 +5,14 @@
 // has 33 rows).  Here the rows stream through a RING of row slots instead: the producer warp
 // issues one TMA bulk copy per (tile, row) in exactly the order the consumers will need them, each
 // slot has its own full/empty mbarrier pair, and a consumer warp releases a slot as soon as it has
-// used the row.  Shared memory per CTA is (slots + parking rows) * 4 KB whatever the tree width (four
-// CTAs per SM for float32, three for float64),
-// threads keep V = 16 B / sizeof(T).  Deferred branches of `c` nodes are parked in shared memory
-// rows indexed by the depth of the deferral (us_walk.cuh): no per-thread stack, no local memory.
+// used the row.  Shared memory per CTA is (slots + parking rows) * slot size whatever the tree width.
+// A thread owns U 16-byte chunks of every row (U * 16 B / sizeof(T) points; chunk u of a slot holds
+// the 256 threads' u-th chunks back to back, so shared-memory loads stay conflict-free and every
+// global store instruction of a warp covers 512 contiguous bytes): the per-row handshake, the
+// descriptor fetch, the kind switch and the loop are paid once per thread and row, so U = 2 halves
+// that overhead per point (it was about half of the float32 kernels' instruction stream).
+// Deferred branches of `c` nodes are parked in shared memory rows indexed by the depth of the
+// deferral (us_walk.cuh): no per-thread stack, no local memory.
 //
 //   to_cartesian    row order per tile: r (if given), then the angle of every node in program order
 //   from_cartesian  two passes over a tile's leaves: c_nodes order for r (sequential sum, bit-exact),
@@ -25,9 +29,8 @@
 namespace us {
 
 constexpr int kMaxRing = 32;         // row slots at most
-constexpr int kRingConsumers = 256;  // consumer threads = points per tile / V
-constexpr int kRingBlock = kRingConsumers + 32;
-constexpr int kRingRowBytes = kRingConsumers * 16;
+// W consumer warps per CTA (4 or 8) + the producer warp; a chunk = the 16 bytes of every consumer thread
+__host__ __device__ constexpr int ring_chunk_bytes(int w) { return w * 32 * 16; }
 
 using RingParams = WalkParams<US_MAX_NODES>;
 
@@ -38,10 +41,37 @@ struct RingShared {
 constexpr int kRingHeader = 512;
 static_assert(sizeof(RingShared) <= kRingHeader, "barrier block");
 
+// V-wide values as U chunks of 16 bytes: chunk u lives ring_chunk_bytes(W) further on in a slot and
+// 256 * V0 points further on in global memory (V0 = 16 / sizeof(T) points per chunk).
+template <typename T, int U, int W>
+__device__ __forceinline__ Vec<T, (16 / (int)sizeof(T)) * U> lds_chunks(uint32_t addr) {
+  constexpr int V0 = 16 / (int)sizeof(T);
+  Vec<T, V0 * U> out;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const Vec<T, V0> c = lds_vec_s<T, V0>(addr + (uint32_t)(u * ring_chunk_bytes(W)));
+#pragma unroll
+    for (int v = 0; v < V0; ++v) out.v[u * V0 + v] = c.v[v];
+  }
+  return out;
+}
+template <typename T, int U, int W>
+__device__ __forceinline__ void stg_chunks(T* dst, const Vec<T, (16 / (int)sizeof(T)) * U>& x) {
+  constexpr int V0 = 16 / (int)sizeof(T);
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    Vec<T, V0> c;
+#pragma unroll
+    for (int v = 0; v < V0; ++v) c.v[v] = x.v[u * V0 + v];
+    stg_vec<T, V0>(dst + u * (W * 32 * V0), c);
+  }
+}
+
 // Consumer side, on shared-space addresses computed once per thread: `mine` already points at this
-// thread's 16 bytes of slot 0, slots are 4 KB apart, barriers 8 bytes apart.
-template <typename T, int V>
+// thread's first 16 bytes of slot 0, slots are U * 4 KB apart, barriers 8 bytes apart.
+template <typename T, int U, int W>
 struct RingConsumer {
+  static constexpr int V = (16 / (int)sizeof(T)) * U;
   uint32_t mine, full, empty;
   uint32_t slot, parity, n_slots;
   bool lane0;
@@ -52,7 +82,7 @@ struct RingConsumer {
     US_ASSERT(slot < n_slots && n_slots <= (uint32_t)kMaxRing);
     used = slot;
     mbar_wait_s(full + slot * 8u, parity);
-    const Vec<T, V> x = lds_vec_s<T, V>(mine + slot * (uint32_t)kRingRowBytes);
+    const Vec<T, V> x = lds_chunks<T, U, W>(mine + slot * (uint32_t)(U * ring_chunk_bytes(W)));
     if (++slot == n_slots) {
       slot = 0u;
       parity ^= 1u;
@@ -72,7 +102,7 @@ struct RingProducer {
   unsigned char* rows;
   uint32_t slot, round, n_slots;
   bool leader;
-  template <typename T>
+  template <uint32_t kRowBytes, typename T>
   __device__ __forceinline__ void put(const T* src, uint64_t policy) {
     if (round > 0u) {
       // one lane polls, the warp reconverges behind it: the copy below is a warp-level (uniform
@@ -81,8 +111,8 @@ struct RingProducer {
       __syncwarp();
     }
     if (leader) {
-      mbar_arrive_expect_tx(&sh->full[slot], (uint32_t)kRingRowBytes);
-      tma_load_row(rows + (size_t)slot * kRingRowBytes, src, (uint32_t)kRingRowBytes, &sh->full[slot], policy);
+      mbar_arrive_expect_tx(&sh->full[slot], kRowBytes);
+      tma_load_row(rows + (size_t)slot * kRowBytes, src, kRowBytes, &sh->full[slot], policy);
     }
     if (++slot == n_slots) {
       slot = 0u;
@@ -91,12 +121,12 @@ struct RingProducer {
   }
 };
 
-__device__ __forceinline__ RingShared* ring_init(unsigned char* smem_raw, int n_slots) {
+__device__ __forceinline__ RingShared* ring_init(unsigned char* smem_raw, int n_slots, int consumer_warps) {
   RingShared* sh = reinterpret_cast<RingShared*>(smem_raw);
   if (threadIdx.x == 0) {
     for (int s = 0; s < n_slots; ++s) {
       mbar_init(&sh->full[s], 1);
-      mbar_init(&sh->empty[s], kRingConsumers / 32);
+      mbar_init(&sh->empty[s], consumer_warps);
     }
     fence_mbar_init();
   }
@@ -105,40 +135,45 @@ __device__ __forceinline__ RingShared* ring_init(unsigned char* smem_raw, int n_
 }
 
 // the parking rows: thread-private columns, plain shared-memory accesses
-template <typename T, int V>
-__device__ __forceinline__ void park_store(uint32_t addr, const Vec<T, V>& x) {
+template <typename T, int U, int W>
+__device__ __forceinline__ void park_store(uint32_t addr, const Vec<T, (16 / (int)sizeof(T)) * U>& x) {
   US_ASSERT(addr % 16u == 0u);
-  uint32_t w[4];
-  memcpy(w, &x, 16);
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+  uint32_t w[4 * U];
+  memcpy(w, &x, 16 * U);
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr + (uint32_t)(u * ring_chunk_bytes(W))), "r"(w[4 * u]), "r"(w[4 * u + 1]),
+                 "r"(w[4 * u + 2]), "r"(w[4 * u + 3])
+                 : "memory");
 }
 
 // =================================================================================================
-template <typename T, int V>
-__global__ void __launch_bounds__(kRingBlock, sizeof(T) == 4 ? 4 : 3) to_cartesian_ring(const __grid_constant__ RingParams p, int64_t n_tiles, int n_slots) {
-  static_assert(sizeof(T) * V == 16, "ring rows are 16 bytes per thread");
-  constexpr int P = kRingConsumers * V;
+template <typename T, int U, int W, int MINB>
+__global__ void __launch_bounds__(W * 32 + 32, MINB) to_cartesian_ring(const __grid_constant__ RingParams p, int64_t n_tiles, int n_slots) {
+  constexpr int V0 = 16 / (int)sizeof(T), V = V0 * U;
+  constexpr int P = W * 32 * V;
+  constexpr uint32_t kRowBytes = (uint32_t)(U * ring_chunk_bytes(W));
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  RingShared* sh = ring_init(smem_raw, n_slots);
+  RingShared* sh = ring_init(smem_raw, n_slots, W);
   unsigned char* rows = smem_raw + kRingHeader;
   const int nn = p.n_nodes;
   const bool has_r = p.has_r != 0;
   const int tid = threadIdx.x;
-  if (warp_index_uniform() == kRingConsumers / 32) {
+  if (warp_index_uniform() == W) {
     const uint64_t policy = policy_evict_first();
     RingProducer prod{sh, rows, 0u, 0u, (uint32_t)n_slots, elect_one()};
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t first = tile * P;
-      if (has_r) prod.put<T>((const T*)p.in[nn] + first, policy);
+      if (has_r) prod.put<kRowBytes, T>((const T*)p.in[nn] + first, policy);
 #pragma unroll 1
-      for (int k = 0; k < nn; ++k) prod.put<T>((const T*)p.in[p.d[k].row_a] + first, policy);
+      for (int k = 0; k < nn; ++k) prod.put<kRowBytes, T>((const T*)p.in[p.d[k].row_a] + first, policy);
     }
     return;
   }
-  RingConsumer<T, V> ring(rows, sh, tid, n_slots);
-  const uint32_t park = smem_u32(rows) + (uint32_t)n_slots * (uint32_t)kRingRowBytes + (uint32_t)tid * 16u;
+  RingConsumer<T, U, W> ring(rows, sh, tid, n_slots);
+  const uint32_t park = smem_u32(rows) + (uint32_t)n_slots * kRowBytes + (uint32_t)tid * 16u;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t g = tile * P + (int64_t)tid * V;
+    const int64_t g = tile * P + (int64_t)tid * V0;
     Vec<T, V> cur;
     if (has_r) {
       uint32_t slot;
@@ -162,54 +197,55 @@ __global__ void __launch_bounds__(kRingBlock, sizeof(T) == 4 ? 4 : 3) to_cartesi
       mul_vec<V>(cur.v, cs.v, pc.v);
       mul_vec<V>(cur.v, sn.v, ps.v);
       const uint32_t kind = d.kind;
-      US_ASSERT(((kind & kNodeKindMask) != US_NODE_C && !(kind & kNodeLinked)) || d.park < (uint32_t)p.max_park * (uint32_t)kRingRowBytes);
-      if ((kind & kNodeKindMask) == US_NODE_C) park_store<T, V>(park + d.park, ps);
+      US_ASSERT(((kind & kNodeKindMask) != US_NODE_C && !(kind & kNodeLinked)) || d.park < (uint32_t)p.max_park * kRowBytes);
+      if ((kind & kNodeKindMask) == US_NODE_C) park_store<T, U, W>(park + d.park, ps);
 #pragma unroll
       for (int v = 0; v < V; ++v) cur.v[v] = ((kind & kNodeKindMask) == US_NODE_B) ? ps.v[v] : pc.v[v];
-      if (kind & kNodeLinked) cur = lds_vec_s<T, V>(park + d.park);
+      if (kind & kNodeLinked) cur = lds_chunks<T, U, W>(park + d.park);
       T* const oc = (T*)d.out_a;
       T* const os = (T*)d.out_b;
-      if (oc) stg_vec<T, V>(oc + g, pc);
-      if (os) stg_vec<T, V>(os + g, ps);
+      if (oc) stg_chunks<T, U, W>(oc + g, pc);
+      if (os) stg_chunks<T, U, W>(os + g, ps);
     }
   }
 }
 
 // =================================================================================================
-template <typename T, int V>
-__global__ void __launch_bounds__(kRingBlock, sizeof(T) == 4 ? 4 : 3) from_cartesian_ring(const __grid_constant__ RingParams p, int64_t n_tiles, int n_slots) {
-  static_assert(sizeof(T) * V == 16, "ring rows are 16 bytes per thread");
-  constexpr int P = kRingConsumers * V;
+template <typename T, int U, int W, int MINB>
+__global__ void __launch_bounds__(W * 32 + 32, MINB) from_cartesian_ring(const __grid_constant__ RingParams p, int64_t n_tiles, int n_slots) {
+  constexpr int V0 = 16 / (int)sizeof(T), V = V0 * U;
+  constexpr int P = W * 32 * V;
+  constexpr uint32_t kRowBytes = (uint32_t)(U * ring_chunk_bytes(W));
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  RingShared* sh = ring_init(smem_raw, n_slots);
+  RingShared* sh = ring_init(smem_raw, n_slots, W);
   unsigned char* rows = smem_raw + kRingHeader;
   const int nn = p.n_nodes;
   const int n_leaves = p.n_rows;
   T* const r_out = (T*)p.r_out;
   const int tid = threadIdx.x;
-  if (warp_index_uniform() == kRingConsumers / 32) {
+  if (warp_index_uniform() == W) {
     const uint64_t keep = policy_evict_last(), drop = policy_evict_first();
     RingProducer prod{sh, rows, 0u, 0u, (uint32_t)n_slots, elect_one()};
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t first = tile * P;
       if (r_out) {
 #pragma unroll 1
-        for (int l = 0; l < n_leaves; ++l) prod.put<T>((const T*)p.in[l] + first, keep);
+        for (int l = 0; l < n_leaves; ++l) prod.put<kRowBytes, T>((const T*)p.in[l] + first, keep);
       }
 #pragma unroll 1
       for (int k = nn - 1; k >= 0; --k) {
         const NodeDesc& d = p.d[k];
         const uint32_t kind = d.kind & kNodeKindMask;
-        if (kind == US_NODE_A || kind == US_NODE_B) prod.put<T>((const T*)p.in[d.row_a] + first, drop);
-        if (kind == US_NODE_A || kind == US_NODE_BP) prod.put<T>((const T*)p.in[d.row_b] + first, drop);
+        if (kind == US_NODE_A || kind == US_NODE_B) prod.put<kRowBytes, T>((const T*)p.in[d.row_a] + first, drop);
+        if (kind == US_NODE_A || kind == US_NODE_BP) prod.put<kRowBytes, T>((const T*)p.in[d.row_b] + first, drop);
       }
     }
     return;
   }
-  RingConsumer<T, V> ring(rows, sh, tid, n_slots);
-  const uint32_t park = smem_u32(rows) + (uint32_t)n_slots * (uint32_t)kRingRowBytes + (uint32_t)tid * 16u;
+  RingConsumer<T, U, W> ring(rows, sh, tid, n_slots);
+  const uint32_t park = smem_u32(rows) + (uint32_t)n_slots * kRowBytes + (uint32_t)tid * 16u;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t g = tile * P + (int64_t)tid * V;
+    const int64_t g = tile * P + (int64_t)tid * V0;
     if (r_out) {
       Vec<T, V> acc;
       for (int l = 0; l < n_leaves; ++l) {
@@ -219,7 +255,7 @@ __global__ void __launch_bounds__(kRingBlock, sizeof(T) == 4 ? 4 : 3) from_carte
         ring.release(slot);
       }
       sqrt_vec<V>(acc.v);
-      stg_vec<T, V>(r_out + g, acc);
+      stg_chunks<T, U, W>(r_out + g, acc);
     }
     Vec<T, V> cur;
 #pragma unroll
@@ -230,8 +266,8 @@ __global__ void __launch_bounds__(kRingBlock, sizeof(T) == 4 ? 4 : 3) from_carte
       Vec<T, V> th, nxt;
       switch (kind & kNodeKindMask) {  // one specialised body per node kind (see from_cartesian_tiled)
         case US_NODE_A: {
-          US_ASSERT(!(kind & kNodeLinked) || d.park < (uint32_t)p.max_park * (uint32_t)kRingRowBytes);
-          if (kind & kNodeLinked) park_store<T, V>(park + d.park, cur);
+          US_ASSERT(!(kind & kNodeLinked) || d.park < (uint32_t)p.max_park * kRowBytes);
+          if (kind & kNodeLinked) park_store<T, U, W>(park + d.park, cur);
           uint32_t slot_c, slot_s;
           const Vec<T, V> vc = ring.get(slot_c);
           const Vec<T, V> vs = ring.get(slot_s);
@@ -255,60 +291,92 @@ __global__ void __launch_bounds__(kRingBlock, sizeof(T) == 4 ? 4 : 3) from_carte
           break;
         }
         default: {
-          US_ASSERT(d.park < (uint32_t)p.max_park * (uint32_t)kRingRowBytes);
-          const Vec<T, V> vs = lds_vec_s<T, V>(park + d.park);
+          US_ASSERT(d.park < (uint32_t)p.max_park * kRowBytes);
+          const Vec<T, V> vs = lds_chunks<T, U, W>(park + d.park);
           node_from_vec<V, true, true>(vs.v, cur.v, th.v, nxt.v);
           break;
         }
       }
       cur = nxt;
       T* o = (T*)d.out_a;
-      if (o) stg_vec<T, V>(o + g, th);
+      if (o) stg_chunks<T, U, W>(o + g, th);
     }
   }
 }
 
 // =================================================================================================
-template <bool TO>
-static const void* ring_fn(int dtype) {
-  if (dtype == US_F32) return TO ? (const void*)&to_cartesian_ring<float, 4> : (const void*)&from_cartesian_ring<float, 4>;
-  return TO ? (const void*)&to_cartesian_ring<double, 2> : (const void*)&from_cartesian_ring<double, 2>;
+// Geometry: U chunks per thread, W consumer warps per CTA, CTAs per SM (which also picks the
+// instantiation whose register budget allows that many).  Defaults from A/B on create_random(32)
+// (tools/ab_inproc.py); the ring_u / ring_w / ring_ctas knobs override them.
+struct RingGeometry {
+  int u, w, ctas;
+};
+int ring_knob(int which);  // 0: ring_ctas, 1: ring_u, 2: ring_w (us_transform_tiled.cu: Tuning)
+
+static RingGeometry ring_geometry(int dtype) {
+  RingGeometry g;
+  g.u = ring_knob(1);
+  if (g.u != 1 && g.u != 2) g.u = 2;
+  g.w = ring_knob(2);
+  if (g.w != 4 && g.w != 8) g.w = 8;
+  if (g.u == 1) g.w = 8;
+  const bool f32 = dtype == US_F32;
+  const int ctas_max = g.u == 1 ? (f32 ? 4 : 3) : g.w == 8 ? (f32 ? 3 : 2) : (f32 ? 5 : 4);
+  g.ctas = ring_knob(0);
+  if (g.ctas <= 0) g.ctas = g.u == 1 ? ctas_max : g.w == 8 ? 2 : 4;
+  if (g.ctas > ctas_max) g.ctas = ctas_max;
+  return g;
 }
 
-int ring_ctas_per_sm();
+template <bool TO, typename T, int U, int W, int MINB>
+static const void* ring_kernel() {
+  return TO ? (const void*)&to_cartesian_ring<T, U, W, MINB> : (const void*)&from_cartesian_ring<T, U, W, MINB>;
+}
+template <bool TO>
+static const void* ring_fn(int dtype, const RingGeometry& g) {
+  if (dtype == US_F32) {
+    if (g.u == 1) return ring_kernel<TO, float, 1, 8, 4>();
+    if (g.w == 4) return ring_kernel<TO, float, 2, 4, 4>();
+    return g.ctas >= 3 ? ring_kernel<TO, float, 2, 8, 3>() : ring_kernel<TO, float, 2, 8, 2>();
+  }
+  if (g.u == 1) return ring_kernel<TO, double, 1, 8, 3>();
+  if (g.w == 4) return ring_kernel<TO, double, 2, 4, 4>();
+  return ring_kernel<TO, double, 2, 8, 2>();
+}
+
+int ring_points_per_tile(int dtype) {
+  const RingGeometry g = ring_geometry(dtype);
+  return g.w * 32 * (16 / (dtype == US_F32 ? 4 : 8)) * g.u;
+}
 
 template <bool TO>
 int launch_ring(const XformParams& p, int dtype, cudaStream_t st, int* points_per_tile) {
-  const int esz = dtype == US_F32 ? 4 : 8;
-  const int P = kRingConsumers * (16 / esz);
+  const RingGeometry g = ring_geometry(dtype);
+  const int P = g.w * 32 * (16 / (dtype == US_F32 ? 4 : 8)) * g.u;
   *points_per_tile = P;
   const int64_t n_tiles = p.n / P;
-  const void* fn = ring_fn<TO>(dtype);
-  // CTAs per SM — four for float32 (<= 56 registers), three for float64; the float32 from_cartesian
-  // is short of warps, not of ring depth: 4 x 8 consumer warps with 8-13 slots each beat 3 x 8
-  // with 16 (3.70 -> 3.53 ms on create_random(32)), and 2 x 8 with 27 slots lose (4.07 ms) — and
-  // row slots: as many as the share of shared memory holds after the parking rows, at least 8
+  const void* fn = ring_fn<TO>(dtype, g);
+  const int block = g.w * 32 + 32;
+  // row slots: as many as the CTA's share of shared memory holds after the parking rows
+  const int row_bytes = g.u * ring_chunk_bytes(g.w);
   const int park_rows = p.plan.max_stack;
-  int ctas = ring_ctas_per_sm();
-  if (ctas <= 0) ctas = dtype == US_F32 ? 4 : 3;
-  if (ctas > (dtype == US_F32 ? 4 : 3)) ctas = dtype == US_F32 ? 4 : 3;
-  int n_slots = ((227 * 1024 / ctas) - 1024 - kRingHeader) / kRingRowBytes - park_rows;
+  int n_slots = ((227 * 1024 / g.ctas) - 1024 - kRingHeader) / row_bytes - park_rows;
   if (n_slots > kMaxRing) n_slots = kMaxRing;
-  if (n_slots < 8) n_slots = 8;
-  const size_t smem = (size_t)kRingHeader + (size_t)(n_slots + park_rows) * kRingRowBytes;
+  if (n_slots < 4) n_slots = 4;
+  const size_t smem = (size_t)kRingHeader + (size_t)(n_slots + park_rows) * row_bytes;
   if (smem > 227u * 1024u) return kNotTaken;
   int per_sm = 0;
-  if (int rc = resident_ctas(fn, smem, kRingBlock, &per_sm)) return rc;
+  if (int rc = resident_ctas(fn, smem, block, &per_sm)) return rc;
   if (per_sm < 1) return kNotTaken;
   int64_t grid = (int64_t)sm_count() * per_sm;
   if (grid > n_tiles) grid = n_tiles;
   static RingParams body;  // 10 KB parameter block: filled under a lock, copied by the launch
   static std::mutex lock;
   std::lock_guard<std::mutex> guard(lock);
-  if (!build_walk<US_MAX_NODES>(p, TO, 1u, (uint32_t)kRingRowBytes, body)) return kNotTaken;
+  if (!build_walk<US_MAX_NODES>(p, TO, 1u, (uint32_t)row_bytes, body)) return kNotTaken;
   int64_t tiles = n_tiles;
   void* args[] = {(void*)&body, (void*)&tiles, (void*)&n_slots};
-  US_CUDA_TRY(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(kRingBlock), args, smem, st), "ring launch");
+  US_CUDA_TRY(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3((unsigned)block), args, smem, st), "ring launch");
   return 0;
 }
 

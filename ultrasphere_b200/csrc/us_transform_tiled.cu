@@ -497,7 +497,9 @@ struct Tuning {
   int bufs = env_int("US_TILE_BUFS", 0);            // buffers in the pool (0: as many as fit)
   int max_rows = env_int("US_TILE_MAX_ROWS", 13);   // wider trees take the row-ring kernels
   int min_tiles = env_int("US_TILED_MIN_TILES", 8); // per SM: smaller batches take the strided kernels
-  int ring_ctas = env_int("US_RING_CTAS", 0);       // resident CTAs per SM the ring kernels size their slots for (0: 4 float32 / 3 float64)
+  int ring_ctas = env_int("US_RING_CTAS", 0);       // resident CTAs per SM the ring kernels size their slots for (0: automatic)
+  int ring_u = env_int("US_RING_U", 0);             // 16-byte chunks of a row per ring consumer thread (0: 2)
+  int ring_w = env_int("US_RING_W", 0);             // consumer warps per ring CTA (0: 8)
 };
 static Tuning& tuning() {
   static Tuning t;
@@ -544,7 +546,7 @@ static int try_tiled(const XformParams& p, int dtype, cudaStream_t st) {
   int n_groups = 0, n_bufs = 0;
   if (!pool_geometry(n_rows, dtype == US_F32 ? max_groups<float>() : max_groups<double>(), &n_groups, &n_bufs)) {
     // wide tree: the rows stream through a ring instead of whole tiles being resident
-    const int ring_p = 256 * (16 / esz);
+    const int ring_p = ring_points_per_tile(dtype);
     if (p.n / ring_p < 2 * sm_count()) return kNotTaken;
     const int rc = launch_ring<TO>(p, dtype, st, &P);
     if (rc != 0) return rc;
@@ -591,7 +593,7 @@ static int try_tiled(const XformParams& p, int dtype, cudaStream_t st) {
   return 0;
 }
 
-int ring_ctas_per_sm() { return tuning().ring_ctas; }
+int ring_knob(int which) { return which == 0 ? tuning().ring_ctas : which == 1 ? tuning().ring_u : tuning().ring_w; }
 
 int set_tile_tuning(const char* name, int value) {
   Tuning& t = tuning();
@@ -599,7 +601,9 @@ int set_tile_tuning(const char* name, int value) {
   else if (!strcmp(name, "tile_bufs")) t.bufs = value;
   else if (!strcmp(name, "tile_max_rows")) t.max_rows = value;
   else if (!strcmp(name, "tiled_min_tiles")) t.min_tiles = value;
-  else if (!strcmp(name, "ring_ctas")) t.ring_ctas = value < 0 ? 0 : (value > 4 ? 4 : value);
+  else if (!strcmp(name, "ring_ctas")) t.ring_ctas = value < 0 ? 0 : (value > 6 ? 6 : value);
+  else if (!strcmp(name, "ring_u")) t.ring_u = (value == 1 || value == 2) ? value : 0;
+  else if (!strcmp(name, "ring_w")) t.ring_w = (value == 4 || value == 8) ? value : 0;
   else return fail(US_EINVAL, "us_set_tuning: unknown knob '%s'", name);
   return 0;
 }
