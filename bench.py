@@ -355,9 +355,9 @@ def run_reference(args: argparse.Namespace, emit) -> None:
 def fp64_instr_per_point(s_ndim: int, c_ndim: int) -> dict:
     """FP64-pipe instructions (DFMA/DMUL/DADD/DSETP) per point of the float64 kernels, counted in
     the source (us_common.cuh) and confirmed by ncu's sm__inst_executed_pipe_fp64:
-    from_cartesian 38 per node (atan2 27 + sqrt 8 + norm 3) plus r (c_ndim squares, c_ndim - 1 adds,
+    from_cartesian 34 per node (atan2 23 + sqrt 8 + norm 3) plus r (c_ndim squares, c_ndim - 1 adds,
     sqrt ~10); to_cartesian 33 per node (sincos 31 + two products)."""
-    return {"from": 38 * s_ndim + 2 * c_ndim + 9, "to": 33 * s_ndim}
+    return {"from": 34 * s_ndim + 2 * c_ndim + 9, "to": 33 * s_ndim}
 
 
 def run_b200(args: argparse.Namespace, emit) -> None:

@@ -87,6 +87,10 @@ def call_to(v):
 
 times = {(v, d): [] for v in variants for d in ("from", "to")}
 block = int(os.environ.get("AB_BLOCK", "0"))  # > 0: sustained mode — blocks of this many back-to-back calls per variant
+# untimed calls of the variant right before each timed block: under the 1000 W cap the SM clock settles
+# to the variant's own power draw only after several hundred milliseconds (tools/clocks_probe.py), so
+# energy differences between variants show only when each one runs alone for that long
+settle = int(os.environ.get("AB_SETTLE", "0"))
 if block:
     for direction, fn in (("from", call_from), ("to", call_to)):
         for v in variants:
@@ -95,6 +99,8 @@ if block:
         for rep in range(reps):
             order = variants if rep % 2 == 0 else variants[::-1]
             for v in order:
+                for _ in range(settle):
+                    fn(v)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 for _ in range(block):

@@ -29,7 +29,9 @@
 namespace us {
 
 constexpr int kMaxRing = 32;         // row slots at most
-// W consumer warps per CTA (4 or 8) + the producer warp; a chunk = the 16 bytes of every consumer thread
+// W consumer warps per CTA + the producer warp (four warps in twice the CTAs measured the same as
+// eight); a chunk = the 16 bytes of every consumer thread
+constexpr int kRingWarps = 8;
 __host__ __device__ constexpr int ring_chunk_bytes(int w) { return w * 32 * 16; }
 
 using RingParams = WalkParams<US_MAX_NODES>;
@@ -305,60 +307,58 @@ __global__ void __launch_bounds__(W * 32 + 32, MINB) from_cartesian_ring(const _
 }
 
 // =================================================================================================
-// Geometry: U chunks per thread, W consumer warps per CTA, CTAs per SM (which also picks the
-// instantiation whose register budget allows that many).  Defaults from A/B on create_random(32)
-// (tools/ab_inproc.py); the ring_u / ring_w / ring_ctas knobs override them.
+// Geometry: U chunks per thread and CTAs per SM (which also picks the instantiation whose register
+// budget allows that many).  Defaults from A/B on create_random(32) under sustained load
+// (tools/ab_inproc.py with AB_SETTLE: the kernels run into the 1000 W cap, so what counts is the
+// time per call once the clocks have settled): U = 2 everywhere; float32 to_cartesian three CTAs per
+// SM (0.89 of the HBM peak against 0.86 with two), from_cartesian two (it wants the deeper ring:
+// 0.73 against 0.70); float64 two.  The ring_u / ring_ctas knobs override.
 struct RingGeometry {
-  int u, w, ctas;
+  int u, ctas;
 };
-int ring_knob(int which);  // 0: ring_ctas, 1: ring_u, 2: ring_w (us_transform_tiled.cu: Tuning)
+int ring_knob(int which);  // 0: ring_ctas, 1: ring_u (us_transform_tiled.cu: Tuning)
 
-static RingGeometry ring_geometry(int dtype) {
+static RingGeometry ring_geometry(int dtype, bool to) {
   RingGeometry g;
   g.u = ring_knob(1);
   if (g.u != 1 && g.u != 2) g.u = 2;
-  g.w = ring_knob(2);
-  if (g.w != 4 && g.w != 8) g.w = 8;
-  if (g.u == 1) g.w = 8;
   const bool f32 = dtype == US_F32;
-  const int ctas_max = g.u == 1 ? (f32 ? 4 : 3) : g.w == 8 ? (f32 ? 3 : 2) : (f32 ? 5 : 4);
+  const int ctas_max = g.u == 1 ? (f32 ? 4 : 3) : (f32 ? 3 : 2);
   g.ctas = ring_knob(0);
-  if (g.ctas <= 0) g.ctas = g.u == 1 ? ctas_max : g.w == 8 ? 2 : 4;
+  if (g.ctas <= 0) g.ctas = g.u == 1 ? ctas_max : (f32 && to) ? 3 : 2;
   if (g.ctas > ctas_max) g.ctas = ctas_max;
   return g;
 }
 
-template <bool TO, typename T, int U, int W, int MINB>
+template <bool TO, typename T, int U, int MINB>
 static const void* ring_kernel() {
-  return TO ? (const void*)&to_cartesian_ring<T, U, W, MINB> : (const void*)&from_cartesian_ring<T, U, W, MINB>;
+  return TO ? (const void*)&to_cartesian_ring<T, U, 8, MINB> : (const void*)&from_cartesian_ring<T, U, 8, MINB>;
 }
 template <bool TO>
 static const void* ring_fn(int dtype, const RingGeometry& g) {
   if (dtype == US_F32) {
-    if (g.u == 1) return ring_kernel<TO, float, 1, 8, 4>();
-    if (g.w == 4) return ring_kernel<TO, float, 2, 4, 4>();
-    return g.ctas >= 3 ? ring_kernel<TO, float, 2, 8, 3>() : ring_kernel<TO, float, 2, 8, 2>();
+    if (g.u == 1) return ring_kernel<TO, float, 1, 4>();
+    return g.ctas >= 3 ? ring_kernel<TO, float, 2, 3>() : ring_kernel<TO, float, 2, 2>();
   }
-  if (g.u == 1) return ring_kernel<TO, double, 1, 8, 3>();
-  if (g.w == 4) return ring_kernel<TO, double, 2, 4, 4>();
-  return ring_kernel<TO, double, 2, 8, 2>();
+  if (g.u == 1) return ring_kernel<TO, double, 1, 3>();
+  return ring_kernel<TO, double, 2, 2>();
 }
 
-int ring_points_per_tile(int dtype) {
-  const RingGeometry g = ring_geometry(dtype);
-  return g.w * 32 * (16 / (dtype == US_F32 ? 4 : 8)) * g.u;
+int ring_points_per_tile(int dtype) {  // the same for both directions
+  const RingGeometry g = ring_geometry(dtype, true);
+  return kRingWarps * 32 * (16 / (dtype == US_F32 ? 4 : 8)) * g.u;
 }
 
 template <bool TO>
 int launch_ring(const XformParams& p, int dtype, cudaStream_t st, int* points_per_tile) {
-  const RingGeometry g = ring_geometry(dtype);
-  const int P = g.w * 32 * (16 / (dtype == US_F32 ? 4 : 8)) * g.u;
+  const RingGeometry g = ring_geometry(dtype, TO);
+  const int P = kRingWarps * 32 * (16 / (dtype == US_F32 ? 4 : 8)) * g.u;
   *points_per_tile = P;
   const int64_t n_tiles = p.n / P;
   const void* fn = ring_fn<TO>(dtype, g);
-  const int block = g.w * 32 + 32;
+  const int block = kRingWarps * 32 + 32;
   // row slots: as many as the CTA's share of shared memory holds after the parking rows
-  const int row_bytes = g.u * ring_chunk_bytes(g.w);
+  const int row_bytes = g.u * ring_chunk_bytes(kRingWarps);
   const int park_rows = p.plan.max_stack;
   int n_slots = ((227 * 1024 / g.ctas) - 1024 - kRingHeader) / row_bytes - park_rows;
   if (n_slots > kMaxRing) n_slots = kMaxRing;

@@ -499,7 +499,6 @@ struct Tuning {
   int min_tiles = env_int("US_TILED_MIN_TILES", 8); // per SM: smaller batches take the strided kernels
   int ring_ctas = env_int("US_RING_CTAS", 0);       // resident CTAs per SM the ring kernels size their slots for (0: automatic)
   int ring_u = env_int("US_RING_U", 0);             // 16-byte chunks of a row per ring consumer thread (0: 2)
-  int ring_w = env_int("US_RING_W", 0);             // consumer warps per ring CTA (0: 8)
 };
 static Tuning& tuning() {
   static Tuning t;
@@ -593,7 +592,7 @@ static int try_tiled(const XformParams& p, int dtype, cudaStream_t st) {
   return 0;
 }
 
-int ring_knob(int which) { return which == 0 ? tuning().ring_ctas : which == 1 ? tuning().ring_u : tuning().ring_w; }
+int ring_knob(int which) { return which == 0 ? tuning().ring_ctas : tuning().ring_u; }
 
 int set_tile_tuning(const char* name, int value) {
   Tuning& t = tuning();
@@ -601,9 +600,8 @@ int set_tile_tuning(const char* name, int value) {
   else if (!strcmp(name, "tile_bufs")) t.bufs = value;
   else if (!strcmp(name, "tile_max_rows")) t.max_rows = value;
   else if (!strcmp(name, "tiled_min_tiles")) t.min_tiles = value;
-  else if (!strcmp(name, "ring_ctas")) t.ring_ctas = value < 0 ? 0 : (value > 6 ? 6 : value);
+  else if (!strcmp(name, "ring_ctas")) t.ring_ctas = value < 0 ? 0 : (value > 4 ? 4 : value);
   else if (!strcmp(name, "ring_u")) t.ring_u = (value == 1 || value == 2) ? value : 0;
-  else if (!strcmp(name, "ring_w")) t.ring_w = (value == 4 || value == 8) ? value : 0;
   else return fail(US_EINVAL, "us_set_tuning: unknown knob '%s'", name);
   return 0;
 }
