@@ -72,6 +72,8 @@ def parse() -> argparse.Namespace:
     ap.add_argument("--no-quadrature", action="store_true", help="skip the integrate() leg (BASELINE configs[4])")
     ap.add_argument("--no-configs", action="store_true", help="skip the C1 / C3 / C4 legs")
     ap.add_argument("--leg-scale", type=float, default=1.0, help="scale the C3 / C4 leg sizes (tests use a small fraction)")
+    ap.add_argument("--no-sustained", action="store_true", help="skip the power-settled (about 1 s of back-to-back calls) timings")
+    ap.add_argument("--sustain-seconds", type=float, default=0.9, help="untimed back-to-back calls before each sustained timing")
     return ap.parse_args()
 
 
@@ -356,8 +358,8 @@ def fp64_instr_per_point(s_ndim: int, c_ndim: int) -> dict:
     """FP64-pipe instructions (DFMA/DMUL/DADD/DSETP) per point of the float64 kernels, counted in
     the source (us_common.cuh) and confirmed by ncu's sm__inst_executed_pipe_fp64:
     from_cartesian 34 per node (atan2 23 + sqrt 8 + norm 3) plus r (c_ndim squares, c_ndim - 1 adds,
-    sqrt ~10); to_cartesian 33 per node (sincos 31 + two products)."""
-    return {"from": 34 * s_ndim + 2 * c_ndim + 9, "to": 33 * s_ndim}
+    sqrt ~10); to_cartesian 32 per node (sincos 30 + two products)."""
+    return {"from": 34 * s_ndim + 2 * c_ndim + 9, "to": 32 * s_ndim}
 
 
 def run_b200(args: argparse.Namespace, emit) -> None:
@@ -394,6 +396,45 @@ def run_b200(args: argparse.Namespace, emit) -> None:
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return [float(v) for v in t.tolist()]
+
+    def sustained_pair(tree, x_in, sph_in, n_pts: int, bytes_per_point: int) -> dict:
+        """Both directions after the clocks have settled.  These kernels draw the board's full 1000 W:
+        within a few hundred milliseconds of back-to-back launches the power cap pulls the SM clock
+        from 1965 MHz to 1.5-1.65 GHz (profiles/r02_clocks_*.json), so a timing of 10-20 steps right
+        after an idle phase (the numbers above) is a burst figure.  Here every direction runs untimed
+        for --sustain-seconds first, then ~0.3 s are timed with NVML sampled next to it."""
+        out = {"how": f"{args.sustain_seconds} s of back-to-back calls untimed, then about 0.3 s timed (CUDA events, max over ranks); clocks = NVML on rank 0 during the timed part"}
+        for direction, fn in (("from_cartesian", lambda: tree.from_cartesian(x_in)), ("to_cartesian", lambda: tree.to_cartesian(sph_in, as_array=True))):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            per = max((time.perf_counter() - t0) / 3, 1e-5)
+            n_settle, n_timed = max(5, int(args.sustain_seconds / per)), max(5, int(0.3 / per))
+            barrier()
+            for _ in range(n_settle):
+                fn()
+            probe = ClockSampler(local)
+            if rank == 0:
+                probe.start()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            w0 = time.perf_counter()
+            s0.record()
+            for _ in range(n_timed):
+                fn()
+            s1.record()
+            torch.cuda.synchronize()
+            probe.window = (w0, time.perf_counter())
+            ck = probe.stop() if rank == 0 else None
+            ms = max_over_ranks([s0.elapsed_time(s1) / n_timed])[0]
+            gbs = n_pts * bytes_per_point / (ms * 1e-3) / 1e9
+            out[direction] = {"ms": ms, "calls_timed": n_timed, "achieved_gbs": gbs, "frac": gbs / peak,
+                              "clocks": None if ck is None else {k: ck.get(k) for k in ("sm_mhz", "sm_max_mhz", "power_w_max", "reasons", "mem_mhz")}}
+        out["value"] = world * n_pts / ((out["from_cartesian"]["ms"] + out["to_cartesian"]["ms"]) * 1e-3)
+        out["unit"] = UNIT
+        return out
 
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(peaks_path):
@@ -438,7 +479,9 @@ def run_b200(args: argparse.Namespace, emit) -> None:
     to_ms = sum(to_each) / args.steps
     total_ms, from_ms, to_ms = max_over_ranks([total_ms, from_ms, to_ms])
     value = world * n * args.steps / (total_ms * 1e-3)
-    del back, sph, x
+    del back
+    headline_sustained = None if args.no_sustained else sustained_pair(c, x, sph, n, 2 * C_NDIM * 4)
+    del sph, x
     torch.cuda.empty_cache()
 
     # The roofline's denominator (MEASURED_PEAKS.json) is a BURST figure: the best of ten isolated
@@ -455,12 +498,23 @@ def run_b200(args: argparse.Namespace, emit) -> None:
             dst.copy_(src)
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
-        copies = 200
+        per_copy = 2 * src.numel() * 2 / (peak * 1e9)
+        settle_copies = 0 if args.no_sustained else int(args.sustain_seconds / per_copy)
+        copies = 200 if args.no_sustained else max(200, int(0.3 / per_copy))
+        for _ in range(settle_copies):
+            dst.copy_(src)
+        probe = ClockSampler(local)
+        if rank == 0:
+            probe.start()
+        torch.cuda.synchronize()
+        w0 = time.perf_counter()
         c0.record()
         for _ in range(copies):
             dst.copy_(src)
         c1.record()
         torch.cuda.synchronize()
+        probe.window = (w0, time.perf_counter())
+        copy_clocks = probe.stop() if rank == 0 else None
         one = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         best = float("inf")
         for _ in range(10):
@@ -474,8 +528,9 @@ def run_b200(args: argparse.Namespace, emit) -> None:
         gb = 2 * src.numel() * 2 / 1e9
         sus = -max_over_ranks([-(gb * copies / (c0.elapsed_time(c1) * 1e-3))])[0]  # the slowest rank's
         sustained = {"sustained_copy_gbs": sus, "burst_copy_gbs": gb / (best * 1e-3), "copies_back_to_back": copies,
-                     "seconds": c0.elapsed_time(c1) * 1e-3,
-                     "how": "torch b.copy_(a) over 1 Gi bf16 elements (read + write bytes): 200 copies back to back vs the best of 10 isolated ones, same run, after the timed steps"}
+                     "seconds": c0.elapsed_time(c1) * 1e-3, "settle_copies_untimed": settle_copies,
+                     "clocks": None if copy_clocks is None else {k: copy_clocks.get(k) for k in ("sm_mhz", "sm_max_mhz", "power_w_max", "reasons", "mem_mhz")},
+                     "how": "torch b.copy_(a) over 1 Gi bf16 elements (read + write bytes): copies back to back after --sustain-seconds of the same untimed vs the best of 10 isolated ones, same run, after the timed steps"}
         del src, dst
         torch.cuda.empty_cache()
     except Exception as exc:
@@ -580,6 +635,8 @@ def run_b200(args: argparse.Namespace, emit) -> None:
                 leg["eager_note"] = "eager calls: at 1 M points the host's per-call work, not the kernel, sets the time"
                 leg["graph_replay"] = {"from_cartesian_ms": gf, "to_cartesian_ms": gt,
                                        "from_frac_hbm": n_leg * bpp / (gf * 1e-3) / 1e9 / peak, "to_frac_hbm": n_leg * bpp / (gt * 1e-3) / 1e9 / peak}
+            if not args.no_sustained and key != "C1":
+                leg["sustained"] = sustained_pair(ct, xs[0], sphs[0], n_leg, bpp)
             configs[key] = leg
             del xs, sphs, back
             torch.cuda.empty_cache()
@@ -785,6 +842,7 @@ def run_b200(args: argparse.Namespace, emit) -> None:
                          "from_cartesian_frac": alg_bytes / (from_ms * 1e-3) / 1e9 / peak, "to_cartesian_frac": alg_bytes / (to_ms * 1e-3) / 1e9 / peak},
         "per_step_ms_rank0": {"from_cartesian": [round(v, 4) for v in from_each], "to_cartesian": [round(v, 4) for v in to_each]},
         "copy_in_this_run": sustained,
+        "sustained": headline_sustained,
         "frac_of_sustained_copy": (achieved / sustained["sustained_copy_gbs"]) if sustained and "sustained_copy_gbs" in sustained else None,
     }
     line = {

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 def test_bench_prints_one_contract_line():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     done = subprocess.run(
-        [sys.executable, os.path.join(root, "bench.py"), "--steps", "3", "--warmup", "3", "--points", "8000000", "--no-cpu-baseline", "--leg-scale", "0.05"],
+        [sys.executable, os.path.join(root, "bench.py"), "--steps", "3", "--warmup", "3", "--points", "8000000", "--no-cpu-baseline", "--leg-scale", "0.05", "--sustain-seconds", "0.1"],
         capture_output=True, text=True, cwd=root, timeout=900,
     )
     assert done.returncode == 0, done.stderr[-3000:]
@@ -40,3 +40,7 @@ def test_bench_prints_one_contract_line():
         leg = legs[key]
         assert leg["from_cartesian_ms"] > 0 and leg["to_cartesian_ms"] > 0 and 0 < leg["roofline"]["from_cartesian"]["frac"] < 1.1, key
     assert legs["C3_hopf3"]["fp64_pipe"]["from_cartesian"]["frac"] > 0 and "graph_replay" in legs["C1"]
+    # the power-settled timings next to the burst ones: headline and every full-size leg
+    for rec in (roof["sustained"], legs["C3_hopf3"]["sustained"], legs["C4"]["sustained"]):
+        assert rec["from_cartesian"]["ms"] > 0 and 0 < rec["to_cartesian"]["frac"] < 1.1 and rec["value"] > 0
+    assert roof["sustained"]["from_cartesian"]["clocks"]["sm_mhz"] > 0

@@ -665,6 +665,39 @@ def test_pool_geometry_does_not_change_the_bits(spec, tdt):
         lib.us_set_tuning(b"tile_bufs", 0)
 
 
+@pytest.mark.parametrize("spec,tdt", [("random:32:0", torch.float32), ("random:32:0", torch.float64), ("hopf:5", torch.float32)])
+def test_ring_geometry_does_not_change_the_bits(spec, tdt):
+    """The row-ring kernels of the wide trees: one or two 16-byte chunks of a row per thread, two to
+    four CTAs per SM (hence ring depths from 4 to 13 slots) — bit-identical results, also against
+    the strided kernels (tile_max_rows = 0 sends every tree through the ring; a small batch through
+    the strided path).  create_hopf(5) (31 angles, stack depth 4) parks the most rows."""
+    from ultrasphere_b200 import _native
+
+    lib = _native.lib()
+    c = make(us, spec)
+    n = 296 * 2048 * 2 + 4 * 321  # enough ring tiles for every geometry, ragged tail for the strided kernel
+    x = torch.rand((c.c_ndim, n), device=DEV, dtype=tdt) * 2 - 1
+    m = 40_000  # below the ring threshold: strided kernels
+    small_s = c.from_cartesian(x[:, :m].contiguous())
+    try:
+        ref_s = ref_x = None
+        for u, ctas in ((0, 0), (1, 0), (1, 2), (2, 2), (2, 3), (1, 4)):
+            assert lib.us_set_tuning(b"ring_u", u) == 0 and lib.us_set_tuning(b"ring_ctas", ctas) == 0
+            s = c.from_cartesian(x)
+            back = c.to_cartesian(s, as_array=True)
+            if ref_s is None:
+                ref_s, ref_x = s, back
+                for k in s:
+                    assert torch.equal(s[k][:m], small_s[k]), ("strided", k)
+                continue
+            for k in ref_s:
+                assert torch.equal(s[k], ref_s[k]), (u, ctas, k)
+            assert torch.equal(back, ref_x), (u, ctas)
+    finally:
+        lib.us_set_tuning(b"ring_u", 0)
+        lib.us_set_tuning(b"ring_ctas", 0)
+
+
 def test_parity_report():
     """The measured error distribution behind the parity claim, per BASELINE config and dtype, on
     2^20 seeded points each: max and 99.99th-percentile distance from the NumPy oracle for r, the

@@ -12,7 +12,7 @@ timeout 1500 python -m pytest tests -x -q -m gpu > $O/${R}_gpu_tests.log 2>&1; t
 timeout 900 python bench.py --impl reference --steps 20 --warmup 5 > $O/bench_${R}_reference.json 2> $O/bench_${R}_reference.err
 timeout 900 python bench.py --steps 20 --warmup 5 > $O/bench_${R}.json 2> $O/bench_${R}.err; tail -1 $O/bench_${R}.err
 # 4. launch list of the bench command (shares, not absolutes)
-SHORT="python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-quadrature --no-configs"
+SHORT="python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-quadrature --no-configs --no-sustained"
 $SHORT > $O/plain_short.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $O/launches_${R}.csv $SHORT > $O/ncu_launches.log 2>&1
 # 5. ncu --set full of the hot kernels at the BASELINE sizes
 cap() {  # name, regex, skip, count, command...
@@ -20,7 +20,7 @@ cap() {  # name, regex, skip, count, command...
   "$@" > $O/plain_$name.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:$re -s $skip -c $cnt -f -o $O/prof_${R}_$name "$@" > $O/ncu_$name.log 2>&1
   tail -1 $O/ncu_$name.log
 }
-cap c2 cartesian_tiled 4 2 python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-quadrature --no-configs
+cap c2 cartesian_tiled 4 2 python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-quadrature --no-configs --no-sustained
 cap hopf3_f64 cartesian_tiled 4 2 python tools/profile_one.py hopf:3 f64 128000000
 cap stdp8_f64 cartesian_tiled 4 2 python tools/profile_one.py standard_prime:8 f64 128000000
 cap ring cartesian_ring 4 2 python tools/profile_one.py random:32:0 f32 64000000
