@@ -146,9 +146,9 @@ __device__ __forceinline__ void stg_vec(T* dst, const Vec<T, V>& x) {
   }
 }
 
-__device__ __forceinline__ uint64_t policy_evict_last() {
+__device__ __forceinline__ uint64_t policy_evict_normal() {
   uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
 
