@@ -548,6 +548,16 @@ def run_b200(args: argparse.Namespace, emit) -> None:
         fma["fp64"], fma["fp32"] = max_over_ranks([-fma["fp64"], -fma["fp32"]])  # min over ranks
         fma = {k: -v for k, v in fma.items()}
         configs["measured_fma_peak_tflops"] = fma
+        # the same probe once the power cap has settled the clocks: ~1 s of back-to-back DFMA launches,
+        # the last call's figure (the denominator for the float64 legs' sustained FP64-pipe fractions)
+        fma_sustained = None
+        if not args.no_sustained:
+            tf = ctypes.c_double()
+            t_end_probe = time.perf_counter() + args.sustain_seconds + 0.3
+            while time.perf_counter() < t_end_probe:
+                _native.check(_native.lib().us_probe_fma_peak(_native.US_F64, 32768, ctypes.byref(tf)), "us_probe_fma_peak")
+            fma_sustained = -max_over_ranks([-tf.value])[0]
+            configs["measured_fma_peak_tflops_sustained"] = {"fp64": fma_sustained, "how": f"us_probe_fma_peak(float64) called back to back for {args.sustain_seconds + 0.3:.1f} s, last call (best of its 3 launches)"}
         leg_steps = max(3, min(args.steps, 10))
         for key, spec, dname, n_leg, what in LEGS:
             tdt = torch.float32 if dname == "f32" else torch.float64
@@ -637,6 +647,14 @@ def run_b200(args: argparse.Namespace, emit) -> None:
                                        "from_frac_hbm": n_leg * bpp / (gf * 1e-3) / 1e9 / peak, "to_frac_hbm": n_leg * bpp / (gt * 1e-3) / 1e9 / peak}
             if not args.no_sustained and key != "C1":
                 leg["sustained"] = sustained_pair(ct, xs[0], sphs[0], n_leg, bpp)
+                if dname == "f64" and fma_sustained:
+                    ipp = fp64_instr_per_point(ct.s_ndim, ct.c_ndim)
+                    pk = fma_sustained / 2 * 1e12
+                    leg["sustained"]["fp64_pipe"] = {
+                        "peak": pk, "peak_source": "measured_fma_peak_tflops_sustained",
+                        "from_cartesian_frac": ipp["from"] * n_leg / (leg["sustained"]["from_cartesian"]["ms"] * 1e-3) / pk,
+                        "to_cartesian_frac": ipp["to"] * n_leg / (leg["sustained"]["to_cartesian"]["ms"] * 1e-3) / pk,
+                    }
             configs[key] = leg
             del xs, sphs, back
             torch.cuda.empty_cache()

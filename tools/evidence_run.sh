@@ -29,4 +29,10 @@ cap c5 "to_cartesian_dot_rows|wreduce_tma|to_cartesian_bcast" 6 3 python tools/p
 # 6. per-call host cost, drift of the headline kernel
 python tools/host_overhead.py > $O/${R}_host_overhead.json 2>&1
 timeout 200 python tools/jitter.py > $O/${R}_jitter.json 2>&1
+# 7. clocks, power and throttle reasons under ~2 s of back-to-back launches (the 1000 W cap)
+python tools/clocks_probe.py standard:9 f32 256000000 2 > $O/${R}_clocks_std9_f32.json 2>> $O/${R}_clocks.err
+python tools/clocks_probe.py hopf:3 f64 128000000 2 > $O/${R}_clocks_hopf3_f64.json 2>> $O/${R}_clocks.err
+python tools/clocks_probe.py random:32:0 f32 64000000 2 > $O/${R}_clocks_ring_f32.json 2>> $O/${R}_clocks.err
+# 8. compute-sanitizer, if this pool lets it run (it has been refused so far: the log says which)
+timeout 600 compute-sanitizer --tool memcheck python tools/sanitize_smoke.py > $O/${R}_memcheck.log 2>&1; echo "memcheck rc=$?" >> $O/${R}_memcheck.log; tail -3 $O/${R}_memcheck.log
 ls -la $O | tail -40

@@ -15,6 +15,8 @@ COPIES = [
     (f"launches_{R}.csv", f"{R}_launches.csv"), ("parity_report.json", f"{R}_parity_report.json"),
     (f"{R}_host_overhead.json", f"{R}_host_overhead.json"), (f"{R}_jitter.json", f"{R}_jitter.json"),
     (f"{R}_checked_smoke.log", f"{R}_checked_smoke.log"), (f"{R}_gpu_tests.log", f"{R}_gpu_tests.log"),
+    (f"{R}_clocks_std9_f32.json", f"{R}_clocks_std9_f32.json"), (f"{R}_clocks_hopf3_f64.json", f"{R}_clocks_hopf3_f64.json"),
+    (f"{R}_clocks_ring_f32.json", f"{R}_clocks_ring_f32.json"), (f"{R}_memcheck.log", f"{R}_memcheck.log"),
 ]
 for src, dst in COPIES:
     if os.path.isfile(os.path.join(G, src)):

@@ -47,5 +47,5 @@ excerpt(r"from_cartesian_tiledIfLi4ELi1E", r"UBLKCP", 26, "producer loop of the 
 excerpt(r"from_cartesian_tiledIfLi4ELi1E", r"VOTE\.ALL", 10, "consumer wait: mbarrier try_wait, warp vote, no divergence")
 excerpt(r"from_cartesian_tiledIfLi4ELi1E", r"MUFU\.RCP", 70, "float32 chain node (V = 4): packed FFMA2 polynomial, MUFU.RCP / MUFU.RSQ seeds, LDS.128 in, STG.E.EF.128 out")
 excerpt(r"from_cartesian_tiledIdLi2ELi4E", r"MUFU\.RCP64H", 60, "float64 create_hopf(3) walk (compile-time recursion): descriptors as constant-bank operands, no stack")
-excerpt(r"from_cartesian_ringIfLi4E", r"STS\.128", 12, "row-ring kernel: a deferred branch parked in shared memory (STS.128), not in local memory")
+excerpt(r"from_cartesian_ringIfLi2ELi8ELi2E", r"STS\.128", 12, "row-ring kernel: a deferred branch parked in shared memory (STS.128), not in local memory")
 excerpt(r"wreduce_tma", r"UBLKCP", 12, "weighted reduction: one TMA bulk copy per slab")
