@@ -653,7 +653,7 @@ def test_pool_geometry_does_not_change_the_bits(spec, tdt):
     ref_s = c.from_cartesian(x)
     ref_x = c.to_cartesian(ref_s, as_array=True)
     try:
-        for groups, bufs in ((1, 2), (2, 3), (3, 7), (5, 6)):
+        for groups, bufs in ((1, 2), (2, 3), (3, 7), (5, 6), (6, 11)):
             assert lib.us_set_tuning(b"tile_groups", groups) == 0 and lib.us_set_tuning(b"tile_bufs", bufs) == 0
             s = c.from_cartesian(x)
             for k in ref_s:
@@ -681,8 +681,9 @@ def test_ring_geometry_does_not_change_the_bits(spec, tdt):
     small_s = c.from_cartesian(x[:, :m].contiguous())
     try:
         ref_s = ref_x = None
-        for u, ctas in ((0, 0), (1, 0), (1, 2), (2, 2), (2, 3), (1, 4)):
+        for u, ctas, slots in ((0, 0, 0), (1, 0, 0), (1, 2, 0), (2, 2, 5), (2, 3, 0), (1, 4, 4), (2, 2, 32)):
             assert lib.us_set_tuning(b"ring_u", u) == 0 and lib.us_set_tuning(b"ring_ctas", ctas) == 0
+            assert lib.us_set_tuning(b"ring_slots", slots) == 0
             s = c.from_cartesian(x)
             back = c.to_cartesian(s, as_array=True)
             if ref_s is None:
@@ -691,11 +692,12 @@ def test_ring_geometry_does_not_change_the_bits(spec, tdt):
                     assert torch.equal(s[k][:m], small_s[k]), ("strided", k)
                 continue
             for k in ref_s:
-                assert torch.equal(s[k], ref_s[k]), (u, ctas, k)
-            assert torch.equal(back, ref_x), (u, ctas)
+                assert torch.equal(s[k], ref_s[k]), (u, ctas, slots, k)
+            assert torch.equal(back, ref_x), (u, ctas, slots)
     finally:
         lib.us_set_tuning(b"ring_u", 0)
         lib.us_set_tuning(b"ring_ctas", 0)
+        lib.us_set_tuning(b"ring_slots", 0)
 
 
 def test_parity_report():

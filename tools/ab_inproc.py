@@ -66,6 +66,7 @@ def apply(v):
         h.us_set_tuning(b"tile_max_rows", 13)
         h.us_set_tuning(b"ring_ctas", 0)
         h.us_set_tuning(b"ring_u", 0)  # libraries older than the knob answer US_EINVAL: ignored
+        h.us_set_tuning(b"ring_slots", 0)
         if knobs:
             for kv in knobs[0].split(","):
                 k, val = kv.split("=")
@@ -91,7 +92,7 @@ block = int(os.environ.get("AB_BLOCK", "0"))  # > 0: sustained mode — blocks o
 # to the variant's own power draw only after several hundred milliseconds (tools/clocks_probe.py), so
 # energy differences between variants show only when each one runs alone for that long
 settle = int(os.environ.get("AB_SETTLE", "0"))
-if block:
+if block > 0:
     for direction, fn in (("from", call_from), ("to", call_to)):
         for v in variants:
             fn(v)
@@ -110,7 +111,27 @@ if block:
                 times[(v, direction)].append(e0.elapsed_time(e1) / block)
         if direction == "from":
             call_from(variants[-1])
-for direction, fn in ((("from", call_from), ("to", call_to)) if not block else ()):
+# AB_BENCH=1: what bench.py (and the driver) does — after an idle second, 5 untimed and 20 timed round
+# trips (from, to, from, to, ...) back to back, per-kernel events; variants alternate per repetition
+if os.environ.get("AB_BENCH"):
+    import time
+    for rep in range(reps):
+        order = variants if rep % 2 == 0 else variants[::-1]
+        for v in order:
+            torch.cuda.synchronize()
+            time.sleep(float(os.environ.get("AB_IDLE", "1.0")))
+            for _ in range(5):
+                call_from(v); call_to(v)
+            evs = []
+            for _ in range(20):
+                e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                e[0].record(); call_from(v); e[1].record(); call_to(v); e[2].record()
+                evs.append(e)
+            torch.cuda.synchronize()
+            times[(v, "from")].append(sum(e[0].elapsed_time(e[1]) for e in evs) / 20)
+            times[(v, "to")].append(sum(e[1].elapsed_time(e[2]) for e in evs) / 20)
+    block = -1
+for direction, fn in ((("from", call_from), ("to", call_to)) if block == 0 else ()):
     for v in variants:
         fn(v)
     torch.cuda.synchronize()
@@ -128,7 +149,7 @@ pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
 if os.path.isfile(pk):
     peak = json.load(open(pk))["hbm_gbs"]
 gb = n * 2 * c.c_ndim * esz / 1e9
-print(f"{spec} {dt} n={n} reps={reps} {'blocks of ' + str(block) + ' back-to-back calls' if block else 'isolated calls'} round-trip max err {err:.2e}")
+print(f"{spec} {dt} n={n} reps={reps} {'blocks of ' + str(block) + ' back-to-back calls' if block > 0 else ('bench pattern: idle, 5 + 20 round trips' if block < 0 else 'isolated calls')} round-trip max err {err:.2e}")
 print("| variant | from median ms (frac) | from best | to median ms (frac) | to best |\n|---|---|---|---|---|")
 for v in variants:
     f, t = times[(v, "from")], times[(v, "to")]

@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(W * 32 + 32, MINB) from_cartesian_ring(const _
 struct RingGeometry {
   int u, ctas;
 };
-int ring_knob(int which);  // 0: ring_ctas, 1: ring_u (us_transform_tiled.cu: Tuning)
+int ring_knob(int which);  // 0: ring_ctas, 1: ring_u, 2: ring_slots (us_transform_tiled.cu: Tuning)
 
 static RingGeometry ring_geometry(int dtype, bool to) {
   RingGeometry g;
@@ -367,6 +367,10 @@ int launch_ring(const XformParams& p, int dtype, cudaStream_t st, int* points_pe
   const int park_rows = p.plan.max_stack;
   int n_slots = ((227 * 1024 / g.ctas) - 1024 - kRingHeader) / row_bytes - park_rows;
   if (n_slots > kMaxRing) n_slots = kMaxRing;
+  // to_cartesian: four slots are enough and measurably better than more (fewer requests in flight:
+  // 0.90-0.91 of the HBM peak against 0.88 with five); from_cartesian wants every slot it can get
+  const int cap = ring_knob(2) > 0 ? ring_knob(2) : (TO ? 4 : kMaxRing);
+  if (n_slots > cap) n_slots = cap;
   if (n_slots < 4) n_slots = 4;
   const size_t smem = (size_t)kRingHeader + (size_t)(n_slots + park_rows) * row_bytes;
   if (smem > 227u * 1024u) return kNotTaken;

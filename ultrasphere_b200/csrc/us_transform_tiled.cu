@@ -499,26 +499,37 @@ struct Tuning {
   int min_tiles = env_int("US_TILED_MIN_TILES", 8); // per SM: smaller batches take the strided kernels
   int ring_ctas = env_int("US_RING_CTAS", 0);       // resident CTAs per SM the ring kernels size their slots for (0: automatic)
   int ring_u = env_int("US_RING_U", 0);             // 16-byte chunks of a row per ring consumer thread (0: 2)
+  int ring_slots = env_int("US_RING_SLOTS", 0);     // cap on the row slots of a ring (0: as many as fit)
 };
 static Tuning& tuning() {
   static Tuning t;
   return t;
 }
 
-// Cut the buffer pool to the tree: S buffers of n_rows 2 KB rows in 227 KB, G groups computing, at
-// least two tiles (and ~48 KB) in flight besides.  false: the tree is too wide for tiles.
+// Cut the buffer pool to the tree: G groups computing, S = G + a little in flight.  On the HBM-bound
+// float32 trees every buffer the consumers are not working on is a tile in flight, and DRAM runs
+// measurably SLOWER under too many outstanding requests: create_standard(9) float32 with the pool
+// filling the 227 KB (S = 11, G = 7: ~200 KB requested per SM, five times the latency-bandwidth
+// product) ran at 0.86-0.89 of the copy peak right after an idle phase and 0.93-0.95 under sustained
+// load; with S = 8 it runs at 0.92-0.98 and 0.92-0.98 (five boxes, tools/ab_inproc.py, AB_BENCH /
+// AB_SETTLE modes; the shallower pools of 5-6 groups gain as much on that tree but lose 4-6 % on
+// create_hopf(3) float32, whose interpreted walk needs the warps).  So: all the groups the register
+// file holds, and 32 KB worth of buffers beyond them (at least one); the float64 trees are
+// compute-bound and indifferent.  false: the tree is too wide for tiles.
 static bool pool_geometry(int n_rows, int g_max, int* n_groups, int* n_bufs) {
   const Tuning& t = tuning();
   if (n_rows > t.max_rows || n_rows > kTileCap + 1) return false;
   const int buf = n_rows * kRowBytes;
-  int s = (kSmemBytes - kPoolHeader) / buf;
-  if (s > kMaxBuffers) s = kMaxBuffers;
-  int in_flight = (48 * 1024 + buf - 1) / buf;
-  if (in_flight < 2) in_flight = 2;
-  int g = s - in_flight;
-  if (g > g_max) g = g_max;
+  int s_fit = (kSmemBytes - kPoolHeader) / buf;
+  if (s_fit > kMaxBuffers) s_fit = kMaxBuffers;
+  int extra = 32 * 1024 / buf;
+  if (extra < 1) extra = 1;
+  int g = g_max;
+  if (g + extra > s_fit) g = s_fit - extra;
   if (t.groups > 0 && t.groups <= g_max) g = t.groups;
-  if (t.bufs > 0 && t.bufs <= s) s = t.bufs;
+  int s = g + extra;
+  if (t.bufs > 0) s = t.bufs;
+  if (s > s_fit) s = s_fit;
   if (g < 1 || s <= g) return false;
   while ((s + g - 1) / g + 1 > kGroupSlots) --s;  // a group never has more tiles outstanding than barriers to announce them on
   *n_groups = g;
@@ -592,7 +603,7 @@ static int try_tiled(const XformParams& p, int dtype, cudaStream_t st) {
   return 0;
 }
 
-int ring_knob(int which) { return which == 0 ? tuning().ring_ctas : tuning().ring_u; }
+int ring_knob(int which) { return which == 0 ? tuning().ring_ctas : which == 1 ? tuning().ring_u : tuning().ring_slots; }
 
 int set_tile_tuning(const char* name, int value) {
   Tuning& t = tuning();
@@ -602,6 +613,7 @@ int set_tile_tuning(const char* name, int value) {
   else if (!strcmp(name, "tiled_min_tiles")) t.min_tiles = value;
   else if (!strcmp(name, "ring_ctas")) t.ring_ctas = value < 0 ? 0 : (value > 4 ? 4 : value);
   else if (!strcmp(name, "ring_u")) t.ring_u = (value == 1 || value == 2) ? value : 0;
+  else if (!strcmp(name, "ring_slots")) t.ring_slots = value < 0 ? 0 : value;
   else return fail(US_EINVAL, "us_set_tuning: unknown knob '%s'", name);
   return 0;
 }
