@@ -1,1 +1,2 @@
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fuzz.py tests/test_gpu_bench_contract.py -x -q -m gpu 2>&1 | tail -3
+O=gpurun_out
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 20 --warmup 5 > $O/bench_r02_8gpu.json 2> $O/bench_r02_8gpu.err; tail -2 $O/bench_r02_8gpu.err
