@@ -152,6 +152,19 @@ def test_argument_errors_do_not_need_a_gpu():
     assert lib.us_quadrature_rules(0, None, None, None, None, None, None, None, None) == 0
 
 
+def test_tuning_knobs_are_named_and_checked():
+    """us_set_tuning is host-only state: every documented knob is accepted (0 = automatic restores the
+    default), anything else is refused with US_EINVAL and a message naming it."""
+    lib = _native.lib()
+    for knob in (b"tile_groups", b"tile_bufs", b"tile_max_rows", b"tiled_min_tiles", b"ring_u", b"ring_ctas", b"ring_slots"):
+        assert lib.us_set_tuning(knob, 2) == 0, knob
+    assert lib.us_set_tuning(b"tile_max_rows", 13) == 0 and lib.us_set_tuning(b"tiled_min_tiles", 8) == 0
+    for knob in (b"tile_groups", b"tile_bufs", b"ring_u", b"ring_ctas", b"ring_slots"):
+        assert lib.us_set_tuning(knob, 0) == 0, knob
+    assert lib.us_set_tuning(b"ring_w", 4) == -1
+    assert b"ring_w" in lib.us_last_error_string()
+
+
 def test_rule_backend_switch_and_rule_parameters():
     from ultrasphere_b200._integral import _rule_parameters
 

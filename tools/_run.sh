@@ -1,2 +1,3 @@
-O=gpurun_out
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 20 --warmup 5 > $O/bench_r02_8gpu.json 2> $O/bench_r02_8gpu.err; tail -2 $O/bench_r02_8gpu.err
+mkdir -p gpurun_out/ab
+V=ab_libs/v30.so
+AB_REPS=200 timeout 300 python tools/ab_inproc.py spherical f64 1000000 $V $V:tiled_min_tiles=64 $V:tile_groups=3 $V:tile_groups=4 $V:tile_groups=5 $V:tile_groups=6,tile_bufs=8 $V:tile_groups=6,tile_bufs=14 $V:tile_groups=4,tile_bufs=8 2>&1 | tee gpurun_out/ab/c1_scan.log
