@@ -1,3 +1,4 @@
-mkdir -p gpurun_out/ab
-V=ab_libs/v30.so
-AB_REPS=200 timeout 300 python tools/ab_inproc.py spherical f64 1000000 $V $V:tiled_min_tiles=64 $V:tile_groups=3 $V:tile_groups=4 $V:tile_groups=5 $V:tile_groups=6,tile_bufs=8 $V:tile_groups=6,tile_bufs=14 $V:tile_groups=4,tile_bufs=8 2>&1 | tee gpurun_out/ab/c1_scan.log
+O=gpurun_out
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 1500 python -m pytest tests -x -q -m gpu > $O/r02_gpu_tests.log 2>&1; tail -2 $O/r02_gpu_tests.log
+timeout 600 python bench.py --steps 20 --warmup 5 > $O/bench_final.json 2> $O/bench_final.err; tail -1 $O/bench_final.err
