@@ -96,11 +96,12 @@ US_API const char* us_last_error_string(void);
 
 /*
  * Tuning / measurement hook, never needed in normal use: overrides how the tile kernels cut their
- * shared-memory pool ("tile_groups", "tile_bufs"; 0 = automatic), from which width on trees take
+ * shared-memory pool ("tile_groups", "tile_bufs"; 0 = automatic) and how many 16-byte chunks of a
+ * row a thread owns ("tile_u": 1 or 2; automatic = 2 for float64 to_cartesian), from which width on trees take
  * the row-ring kernels ("tile_max_rows"), the small-batch cut-over ("tiled_min_tiles", per SM), and
  * the ring kernels' geometry: 16-byte chunks of a row per thread ("ring_u": 1 or 2), CTAs per SM
  * their slots are sized for ("ring_ctas") and a cap on the row slots ("ring_slots"); 0 = automatic.
- * The same knobs are read from US_TILE_GROUPS, US_TILE_BUFS, US_TILE_MAX_ROWS, US_TILED_MIN_TILES,
+ * The same knobs are read from US_TILE_GROUPS, US_TILE_BUFS, US_TILE_U, US_TILE_MAX_ROWS, US_TILED_MIN_TILES,
  * US_RING_U, US_RING_CTAS, US_RING_SLOTS at first use.  Process-wide; results never depend on it,
  * only speed.
  */

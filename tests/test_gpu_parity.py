@@ -653,8 +653,9 @@ def test_pool_geometry_does_not_change_the_bits(spec, tdt):
     ref_s = c.from_cartesian(x)
     ref_x = c.to_cartesian(ref_s, as_array=True)
     try:
-        for groups, bufs in ((1, 2), (2, 3), (3, 7), (5, 6), (6, 11)):
+        for groups, bufs, u in ((1, 2, 0), (2, 3, 1), (3, 7, 2), (5, 6, 1), (6, 11, 0), (4, 5, 2)):
             assert lib.us_set_tuning(b"tile_groups", groups) == 0 and lib.us_set_tuning(b"tile_bufs", bufs) == 0
+            assert lib.us_set_tuning(b"tile_u", u) == 0
             s = c.from_cartesian(x)
             for k in ref_s:
                 assert torch.equal(s[k], ref_s[k]), (groups, bufs, k)
@@ -663,6 +664,7 @@ def test_pool_geometry_does_not_change_the_bits(spec, tdt):
     finally:
         lib.us_set_tuning(b"tile_groups", 0)
         lib.us_set_tuning(b"tile_bufs", 0)
+        lib.us_set_tuning(b"tile_u", 0)
 
 
 @pytest.mark.parametrize("spec,tdt", [("random:32:0", torch.float32), ("random:32:0", torch.float64), ("hopf:5", torch.float32)])
@@ -698,6 +700,39 @@ def test_ring_geometry_does_not_change_the_bits(spec, tdt):
         lib.us_set_tuning(b"ring_u", 0)
         lib.us_set_tuning(b"ring_ctas", 0)
         lib.us_set_tuning(b"ring_slots", 0)
+
+
+@pytest.mark.parametrize("spec,tdt,n,knobs", [
+    ("random:32:0", torch.float32, 64_000_000, {}),
+    ("random:32:0", torch.float32, 64_000_000, {b"ring_slots": 4, b"ring_ctas": 3}),
+    ("random:32:0", torch.float64, 32_000_000, {}),
+    ("standard:9", torch.float32, 256_000_000, {}),
+])
+def test_back_to_back_launches_are_deterministic(spec, tdt, n, knobs):
+    """from_cartesian and to_cartesian launched back to back, over and over, at the BASELINE sizes:
+    every repetition must reproduce the first one bit for bit.  This is the test that catches a
+    shared-memory slot handed back to the TMA producer too early (a refill overtaking a queued load
+    shows up as a few dozen wrong points in ~10^9, only with shallow rings and only now and then)."""
+    from ultrasphere_b200 import _native
+
+    lib = _native.lib()
+    c = make(us, spec)
+    x = torch.rand((c.c_ndim, n), device=DEV, dtype=tdt, generator=torch.Generator(device=DEV).manual_seed(99)).mul_(2).sub_(1)
+    try:
+        for k, v in knobs.items():
+            assert lib.us_set_tuning(k, v) == 0
+        s0 = c.from_cartesian(x)
+        y0 = c.to_cartesian(s0, as_array=True)
+        for rep in range(25):
+            s = c.from_cartesian(x)
+            y = c.to_cartesian(s, as_array=True)
+            assert torch.equal(y, y0), (spec, rep, int((y != y0).any(0).sum()))
+            for k in s0:
+                assert torch.equal(s[k], s0[k]), (spec, rep, k)
+    finally:
+        for k in knobs:
+            lib.us_set_tuning(k, 0)
+        torch.cuda.empty_cache()
 
 
 def test_parity_report():

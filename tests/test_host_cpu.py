@@ -156,13 +156,31 @@ def test_tuning_knobs_are_named_and_checked():
     """us_set_tuning is host-only state: every documented knob is accepted (0 = automatic restores the
     default), anything else is refused with US_EINVAL and a message naming it."""
     lib = _native.lib()
-    for knob in (b"tile_groups", b"tile_bufs", b"tile_max_rows", b"tiled_min_tiles", b"ring_u", b"ring_ctas", b"ring_slots"):
+    for knob in (b"tile_groups", b"tile_bufs", b"tile_u", b"tile_max_rows", b"tiled_min_tiles", b"ring_u", b"ring_ctas", b"ring_slots"):
         assert lib.us_set_tuning(knob, 2) == 0, knob
     assert lib.us_set_tuning(b"tile_max_rows", 13) == 0 and lib.us_set_tuning(b"tiled_min_tiles", 8) == 0
-    for knob in (b"tile_groups", b"tile_bufs", b"ring_u", b"ring_ctas", b"ring_slots"):
+    for knob in (b"tile_groups", b"tile_bufs", b"tile_u", b"ring_u", b"ring_ctas", b"ring_slots"):
         assert lib.us_set_tuning(knob, 0) == 0, knob
     assert lib.us_set_tuning(b"ring_w", 4) == -1
     assert b"ring_w" in lib.us_last_error_string()
+
+
+def test_no_slot_is_released_before_its_loads_return():
+    """Static check of the shipped SASS (tools/sass_release_scan.py): in every TMA-staged kernel a
+    consumer's mbarrier arrive — the one that hands a shared-memory slot back to the producer — sits
+    behind an instruction that reads the registers loaded from that slot, so in-order issue holds it
+    until the loads have returned.  Without that, a refill was seen to overtake a queued load (the
+    ring kernels' r row: a few dozen wrong points per 10^9, tools/stress.py)."""
+    import shutil
+    import subprocess
+    import sys
+
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    done = subprocess.run([sys.executable, os.path.join(root, "tools", "sass_release_scan.py")], capture_output=True, text=True, timeout=600)
+    assert done.returncode == 0, done.stdout[-3000:]
+    assert "release-before-use: 0 of" in done.stdout and "from_cartesian_ring" in done.stdout and "wreduce_tma" in done.stdout
 
 
 def test_rule_backend_switch_and_rule_parameters():

@@ -61,7 +61,7 @@ def apply(v):
     path, *knobs = v.split(":")
     h = libs[path]
     if hasattr(h, "us_set_tuning"):
-        for name in ("tile_groups", "tile_bufs"):
+        for name in ("tile_groups", "tile_bufs", "tile_u"):
             h.us_set_tuning(name.encode(), 0)
         h.us_set_tuning(b"tile_max_rows", 13)
         h.us_set_tuning(b"ring_ctas", 0)

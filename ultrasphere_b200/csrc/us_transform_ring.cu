@@ -75,13 +75,15 @@ __device__ __forceinline__ void stg_chunks(T* dst, const Vec<T, (16 / (int)sizeo
 // thread's first 16 bytes of slot 0, slots are U * 4 KB apart, barriers 8 bytes apart.
 template <typename T, int U, int W>
 struct RingConsumer {
-  static constexpr int V = (16 / (int)sizeof(T)) * U;
+  static constexpr int V0 = 16 / (int)sizeof(T);
+  static constexpr int V = V0 * U;
   uint32_t mine, full, empty;
   uint32_t slot, parity, n_slots;
+  uint32_t zero;  // 0 at run time, unknown at compile time (WalkParams::zero)
   bool lane0;
-  __device__ __forceinline__ RingConsumer(const unsigned char* rows, RingShared* sh, int tid, int slots)
+  __device__ __forceinline__ RingConsumer(const unsigned char* rows, RingShared* sh, int tid, int slots, int zero_)
       : mine(smem_u32(rows) + (uint32_t)tid * 16u), full(smem_u32(&sh->full[0])), empty(smem_u32(&sh->empty[0])),
-        slot(0u), parity(0u), n_slots((uint32_t)slots), lane0((tid & 31) == 0) {}
+        slot(0u), parity(0u), n_slots((uint32_t)slots), zero((uint32_t)zero_), lane0((tid & 31) == 0) {}
   __device__ __forceinline__ Vec<T, V> get(uint32_t& used) {
     US_ASSERT(slot < n_slots && n_slots <= (uint32_t)kMaxRing);
     used = slot;
@@ -93,9 +95,24 @@ struct RingConsumer {
     }
     return x;
   }
-  __device__ __forceinline__ void release(uint32_t used) {
+  // Hand the slot back — AFTER this warp's loads from it have returned.  Nothing in the memory model
+  // orders a plain ld.shared before a later mbarrier.arrive of the same thread in the shared-memory
+  // pipeline, and ptxas is free to issue the arrive right behind the loads (it did, for the r rows):
+  // with a shallow ring the producer's refill of the slot was then seen to overtake a load still
+  // queued — a few dozen points per 10^9 with another row's values (tools/stress.py, three CTAs per
+  // SM with four or five slots).  So the barrier address is made to depend on one register of every
+  // 16-byte load (`& zero`: always 0, but ptxas cannot know): in-order issue then holds the arrive
+  // until the loads' scoreboards clear.  Two integer instructions per chunk.
+  __device__ __forceinline__ void release(uint32_t used, const Vec<T, V>& x) {
+    uint32_t dep = 0u;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      uint32_t w;
+      memcpy(&w, &x.v[u * V0], 4);
+      dep |= w;
+    }
     __syncwarp();
-    if (lane0) mbar_arrive_s(empty + used * 8u);
+    if (lane0) mbar_arrive_s(empty + used * 8u + (dep & zero));
   }
 };
 
@@ -174,7 +191,7 @@ __global__ void __launch_bounds__(W * 32 + 32, MINB) to_cartesian_ring(const __g
     }
     return;
   }
-  RingConsumer<T, U, W> ring(rows, sh, tid, n_slots);
+  RingConsumer<T, U, W> ring(rows, sh, tid, n_slots, p.zero);
   const uint32_t park = smem_u32(rows) + (uint32_t)n_slots * kRowBytes + (uint32_t)tid * 16u;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t g = tile * P + (int64_t)tid * V0;
@@ -182,11 +199,7 @@ __global__ void __launch_bounds__(W * 32 + 32, MINB) to_cartesian_ring(const __g
     if (has_r) {
       uint32_t slot;
       cur = ring.get(slot);
-      // the row is in registers once it has been used; `cur` is consumed by the first product
-      // below, but the slot can go back right away: force the use with a register barrier
-#pragma unroll
-      for (int v = 0; v < V; ++v) asm volatile("" ::"r"(*reinterpret_cast<const uint32_t*>(&cur.v[v])));
-      ring.release(slot);
+      ring.release(slot, cur);  // tied to the loaded registers (RingConsumer::release): `cur` is first consumed much later
     } else {
 #pragma unroll
       for (int v = 0; v < V; ++v) cur.v[v] = T(1);
@@ -197,7 +210,7 @@ __global__ void __launch_bounds__(W * 32 + 32, MINB) to_cartesian_ring(const __g
       const Vec<T, V> th = ring.get(slot);
       Vec<T, V> pc, ps, sn, cs;
       sincos_vec<V>(th.v, sn.v, cs.v);
-      ring.release(slot);  // after the sincos consumed the angles
+      ring.release(slot, th);  // after the sincos consumed the angles
       mul_vec<V>(cur.v, cs.v, pc.v);
       mul_vec<V>(cur.v, sn.v, ps.v);
       const uint32_t kind = d.kind;
@@ -249,7 +262,7 @@ __global__ void __launch_bounds__(W * 32 + 32, MINB) from_cartesian_ring(const _
     }
     return;
   }
-  RingConsumer<T, U, W> ring(rows, sh, tid, n_slots);
+  RingConsumer<T, U, W> ring(rows, sh, tid, n_slots, p.zero);
   const uint32_t park = smem_u32(rows) + (uint32_t)n_slots * kRowBytes + (uint32_t)tid * 16u;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t g = tile * P + (int64_t)tid * V0;
@@ -259,7 +272,7 @@ __global__ void __launch_bounds__(W * 32 + 32, MINB) from_cartesian_ring(const _
         uint32_t slot;
         const Vec<T, V> x = ring.get(slot);
         sumsq_step<V>(acc.v, x.v, l == 0);
-        ring.release(slot);
+        ring.release(slot, x);
       }
       sqrt_vec<V>(acc.v);
       stg_chunks<T, U, W>(r_out + g, acc);
@@ -279,22 +292,22 @@ __global__ void __launch_bounds__(W * 32 + 32, MINB) from_cartesian_ring(const _
           const Vec<T, V> vc = ring.get(slot_c);
           const Vec<T, V> vs = ring.get(slot_s);
           node_from_vec<V, false, false>(vs.v, vc.v, th.v, nxt.v);
-          ring.release(slot_c);
-          ring.release(slot_s);
+          ring.release(slot_c, vc);
+          ring.release(slot_s, vs);
           break;
         }
         case US_NODE_B: {
           uint32_t slot_c;
           const Vec<T, V> vc = ring.get(slot_c);
           node_from_vec<V, true, false>(cur.v, vc.v, th.v, nxt.v);
-          ring.release(slot_c);
+          ring.release(slot_c, vc);
           break;
         }
         case US_NODE_BP: {
           uint32_t slot_s;
           const Vec<T, V> vs = ring.get(slot_s);
           node_from_vec<V, false, true>(vs.v, cur.v, th.v, nxt.v);
-          ring.release(slot_s);
+          ring.release(slot_s, vs);
           break;
         }
         default: {

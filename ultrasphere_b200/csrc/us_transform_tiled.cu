@@ -44,11 +44,16 @@ constexpr int kGroupWarps = kGroupThreads / 32;
 constexpr int kMaxBuffers = 32;
 constexpr int kTileCap = 16;              // rows per tile the tile kernels are compiled for
 constexpr int kSmemBytes = 227 * 1024;    // dynamic shared memory one CTA may ask for on sm_100
-constexpr int kRowBytes = kGroupThreads * 16;
+constexpr int kRowBytes = kGroupThreads * 16;  // one 16-byte chunk of every thread of a group: a row of a tile is U of these
+// A thread owns U chunks of every row (V = U * 16 / sizeof(T) points).  U = 2 exists for float64
+// only: those kernels are bound by instruction issue and, in a long run, by the energy per point
+// (DESIGN.md §4.0), and the per-thread work that does not depend on V — descriptor fetches, the
+// walk's control flow, addresses, barrier handshakes — halves per point.
 // groups per CTA: 1 + 4 G warps must fit the register file (64 K registers) at the kernels'
-// register counts — float32 <= 64 registers, float64 <= 80
-template <typename T>
-constexpr int max_groups() { return sizeof(T) == 4 ? 7 : 6; }
+// register counts — float32 <= 64 registers, float64 <= 80; U = 2: float64 four groups (17 warps, five
+// of them on one scheduler's 16 K registers: <= 96), float32 five (six on one scheduler: <= 80)
+template <typename T, int U = 1>
+constexpr int max_groups() { return U == 2 ? (sizeof(T) == 4 ? 5 : 4) : (sizeof(T) == 4 ? 7 : 6); }
 
 using TileParams = WalkParams<kTileCap>;
 
@@ -66,10 +71,11 @@ static_assert((kGroupSlots & (kGroupSlots - 1)) == 0, "slot count is a power of 
 // addresses), waits until the buffer it is about to overwrite has been released, and its elected
 // lane issues the tile's copies (UBLKCP takes uniform operands; spreading the rows over lanes
 // would only serialise them again).
-template <typename T>
+template <typename T, int U>
 __device__ __forceinline__ void producer_loop(const TileParams& p, unsigned char* bufs, uint32_t buf_bytes, int n_groups, int n_bufs,
                                               int64_t n_tiles, int tail_points, PoolShared* sh) {
-  constexpr int P = kGroupThreads * (16 / (int)sizeof(T));
+  constexpr int P = kGroupThreads * (16 / (int)sizeof(T)) * U;
+  constexpr uint32_t kTileRowBytes = (uint32_t)(kRowBytes * U);
   const bool leader = elect_one();
   const uint64_t policy = policy_evict_first();
   const int n_rows = p.n_rows;
@@ -85,13 +91,13 @@ __device__ __forceinline__ void producer_loop(const TileParams& p, unsigned char
     unsigned char* dst = bufs + (size_t)b * buf_bytes;
     uint64_t* bar = &sh->full[g][slot];
     // the ragged last tile (tail_points > 0) copies only the bytes that exist: a multiple of 16
-    const uint32_t row_bytes = (tail_points > 0 && tile == n_tiles - 1) ? (uint32_t)tail_points * (uint32_t)sizeof(T) : (uint32_t)kRowBytes;
+    const uint32_t row_bytes = (tail_points > 0 && tile == n_tiles - 1) ? (uint32_t)tail_points * (uint32_t)sizeof(T) : kTileRowBytes;
     if (leader) mbar_arrive_expect_tx(bar, (uint32_t)n_rows * row_bytes);
     const int64_t first = tile * P;
 #pragma unroll 4
     for (int row = 0; row < n_rows; ++row) {
       const T* src = (const T*)p.in[row] + first;
-      if (leader) tma_load_row(dst + (size_t)row * kRowBytes, src, row_bytes, bar, policy);
+      if (leader) tma_load_row(dst + (size_t)row * kTileRowBytes, src, row_bytes, bar, policy);
     }
     if (++b == n_bufs) {
       b = 0;
@@ -108,15 +114,56 @@ __device__ __forceinline__ void producer_loop(const TileParams& p, unsigned char
 // overwrites the buffer with the next tile: generic proxy -> async proxy.
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// V-wide access to a thread's part of a row: chunk u sits kRowBytes further on in the row (shared
+// memory) and kGroupThreads * V0 points further on in the arrays (V0 = points per 16-byte chunk), so
+// that loads stay conflict-free and every store instruction of a warp covers 512 contiguous bytes.
 template <typename T, int V>
 __device__ __forceinline__ Vec<T, V> lds_at(const unsigned char* mine, uint32_t row_off) {
-  US_ASSERT(row_off % kRowBytes == 0 && row_off < (kTileCap + 1) * kRowBytes);  // a whole row of this thread's tile
-  return *reinterpret_cast<const Vec<T, V>*>(mine + row_off);
+  constexpr int V0 = 16 / (int)sizeof(T), U = V / V0;
+  US_ASSERT(row_off % (kRowBytes * U) == 0 && row_off < (kTileCap + 1) * kRowBytes * U);  // a whole row of this thread's tile
+  Vec<T, V> out;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const Vec<T, V0> c = *reinterpret_cast<const Vec<T, V0>*>(mine + row_off + u * kRowBytes);
+#pragma unroll
+    for (int v = 0; v < V0; ++v) out.v[u * V0 + v] = c.v[v];
+  }
+  return out;
 }
 template <typename T, int V>
 __device__ __forceinline__ void sts_at(unsigned char* mine, uint32_t row_off, const Vec<T, V>& x) {
-  US_ASSERT(row_off % kRowBytes == 0 && row_off < (kTileCap + 1) * kRowBytes);
-  *reinterpret_cast<Vec<T, V>*>(mine + row_off) = x;
+  constexpr int V0 = 16 / (int)sizeof(T), U = V / V0;
+  US_ASSERT(row_off % (kRowBytes * U) == 0 && row_off < (kTileCap + 1) * kRowBytes * U);
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    Vec<T, V0> c;
+#pragma unroll
+    for (int v = 0; v < V0; ++v) c.v[v] = x.v[u * V0 + v];
+    *reinterpret_cast<Vec<T, V0>*>(mine + row_off + u * kRowBytes) = c;
+  }
+}
+// `live`: bit u set = chunk u of this thread lies inside the batch (all ones except in a ragged last tile)
+template <typename T, int V>
+__device__ __forceinline__ void stg_tile(T* dst, const Vec<T, V>& x, uint32_t live) {
+  constexpr int V0 = 16 / (int)sizeof(T), U = V / V0;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    Vec<T, V0> c;
+#pragma unroll
+    for (int v = 0; v < V0; ++v) c.v[v] = x.v[u * V0 + v];
+    if (U == 1 || (live >> u) & 1u) stg_vec<T, V0>(dst + u * (kGroupThreads * V0), c);
+  }
+}
+template <typename T, int V>
+__device__ __forceinline__ uint32_t live_chunks(int t, int64_t tile, int64_t n_tiles, int tail_points) {
+  constexpr int V0 = 16 / (int)sizeof(T), U = V / V0;
+  if (tail_points == 0 || tile != n_tiles - 1) return (1u << U) - 1u;
+  // in the ragged last tile a chunk holds V0 whole points or none (the tail is a multiple of 16 bytes)
+  uint32_t m = 0;
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    if (u * (kGroupThreads * V0) + t * V0 < tail_points) m |= 1u << u;
+  return m;
 }
 
 // Position of a consumer group in the tile sequence of its CTA: its j-th tile is tile
@@ -154,18 +201,20 @@ __device__ __forceinline__ PoolShared* pool_init(unsigned char* smem_raw, int n_
 // to_cartesian
 // =================================================================================================
 template <typename T, int V>
-__global__ void __launch_bounds__(32 + kGroupThreads * max_groups<T>(), 1)
+__global__ void __launch_bounds__(32 + kGroupThreads * max_groups<T, V * (int)sizeof(T) / 16>(), 1)
     to_cartesian_tiled(const __grid_constant__ TileParams p, int64_t n_tiles, int n_groups, int n_bufs, int tail_points) {
   constexpr int P = kGroupThreads * V;
+  constexpr int V0 = 16 / (int)sizeof(T), U = V / V0;
+  constexpr uint32_t kTileRowBytes = (uint32_t)(kRowBytes * U);
   extern __shared__ __align__(128) unsigned char smem_raw[];
   PoolShared* sh = pool_init(smem_raw, n_groups, n_bufs);
   unsigned char* bufs = smem_raw + kPoolHeader;
   const int nn = p.n_nodes;
-  const uint32_t buf_bytes = (uint32_t)p.n_rows * (uint32_t)kRowBytes;
+  const uint32_t buf_bytes = (uint32_t)p.n_rows * kTileRowBytes;
   const int tid = threadIdx.x;
   const int warp = warp_index_uniform();
   if (warp == 0) {
-    producer_loop<T>(p, bufs, buf_bytes, n_groups, n_bufs, n_tiles, tail_points, sh);
+    producer_loop<T, U>(p, bufs, buf_bytes, n_groups, n_bufs, n_tiles, tail_points, sh);
     return;
   }
   const int t = (tid - 32) & (kGroupThreads - 1);
@@ -176,13 +225,12 @@ __global__ void __launch_bounds__(32 + kGroupThreads * max_groups<T>(), 1)
     US_ASSERT(group < n_groups && at.b >= 0 && at.b < n_bufs && at.slot >= 0 && at.slot < kGroupSlots);
     US_ASSERT(kPoolHeader + (size_t)(at.b + 1) * buf_bytes <= (size_t)kSmemBytes);
     mbar_wait(&sh->full[group][at.slot], at.parity);
-    const int64_t g = at.tile * P + (int64_t)t * V;
-    // in the ragged last tile a thread either owns V whole points or none (the tail is a multiple of 16 bytes)
-    const bool live = tail_points == 0 || at.tile != n_tiles - 1 || t * V < tail_points;
+    const int64_t g = at.tile * P + (int64_t)t * V0;
+    const uint32_t live = live_chunks<T, V>(t, at.tile, n_tiles, tail_points);
     if (live) {
     Vec<T, V> cur;
     if (has_r) {
-      cur = lds_at<T, V>(mine, (uint32_t)nn * kRowBytes);
+      cur = lds_at<T, V>(mine, (uint32_t)nn * kTileRowBytes);
     } else {
 #pragma unroll
       for (int v = 0; v < V; ++v) cur.v[v] = T(1);
@@ -208,8 +256,8 @@ __global__ void __launch_bounds__(32 + kGroupThreads * max_groups<T>(), 1)
       if (kind & kNodeLinked) cur = lds_at<T, V>(mine, d.park);
       T* const oc = (T*)d.out_a;
       T* const os = (T*)d.out_b;
-      if (oc) stg_vec<T, V>(oc + g, pc);
-      if (os) stg_vec<T, V>(os + g, ps);
+      if (oc) stg_tile<T, V>(oc + g, pc, live);
+      if (os) stg_tile<T, V>(os + g, ps, live);
       th = th_next;
     }
     }
@@ -224,7 +272,7 @@ __global__ void __launch_bounds__(32 + kGroupThreads * max_groups<T>(), 1)
 // make, so the values do not depend on which kernel ran).  Out of line: points with zero, tiny,
 // huge or non-finite coordinates only.
 template <typename T, int V, int CHAIN>
-__device__ __noinline__ void chain_redo(const TileParams& p, const unsigned char* mine, int64_t g) {
+__device__ __noinline__ void chain_redo(const TileParams& p, const unsigned char* mine, int64_t g, uint32_t live) {
   const int nn = p.n_nodes;
   Vec<T, V> cur;
   {
@@ -234,7 +282,7 @@ __device__ __noinline__ void chain_redo(const TileParams& p, const unsigned char
     Vec<T, V> th;
     node_from_vec<V>(vs.v, vc.v, th.v, cur.v);
     T* o = (T*)d.out_a;
-    if (o) stg_vec<T, V>(o + g, th);
+    if (o) stg_tile<T, V>(o + g, th, live);
   }
 #pragma unroll 1
   for (int k = nn - 2; k >= 0; --k) {
@@ -247,7 +295,7 @@ __device__ __noinline__ void chain_redo(const TileParams& p, const unsigned char
       node_from_vec<V, false, true>(leaf.v, cur.v, th.v, nxt.v);
     cur = nxt;
     T* o = (T*)d.out_a;
-    if (o) stg_vec<T, V>(o + g, th);
+    if (o) stg_tile<T, V>(o + g, th, live);
   }
 }
 
@@ -258,7 +306,7 @@ __device__ __noinline__ void chain_redo(const TileParams& p, const unsigned char
 // partial norms stay in registers (no parking, no kind switch, no moves at the switch's merge
 // point), and the two sub-evaluations are independent chains the scheduler can interleave.
 template <typename T, int V, int Q, int I>
-__device__ __forceinline__ Vec<T, V> hopf_norm(const TileParams& p, const unsigned char* mine, int64_t g) {
+__device__ __forceinline__ Vec<T, V> hopf_norm(const TileParams& p, const unsigned char* mine, int64_t g, uint32_t live) {
   const NodeDesc& d = p.d[I];
   Vec<T, V> th, nrm;
   if constexpr (Q == 1) {  // `a`: two leaves
@@ -266,12 +314,12 @@ __device__ __forceinline__ Vec<T, V> hopf_norm(const TileParams& p, const unsign
     const Vec<T, V> vs = lds_at<T, V>(mine, d.row_b);
     node_from_vec<V, false, false>(vs.v, vc.v, th.v, nrm.v);
   } else {  // `c`: two subtree norms (>= 0)
-    const Vec<T, V> nc = hopf_norm<T, V, Q - 1, I + 1>(p, mine, g);
-    const Vec<T, V> ns = hopf_norm<T, V, Q - 1, I + (1 << (Q - 1))>(p, mine, g);
+    const Vec<T, V> nc = hopf_norm<T, V, Q - 1, I + 1>(p, mine, g, live);
+    const Vec<T, V> ns = hopf_norm<T, V, Q - 1, I + (1 << (Q - 1))>(p, mine, g, live);
     node_from_vec<V, true, true>(ns.v, nc.v, th.v, nrm.v);
   }
   T* o = (T*)d.out_a;
-  if (o) stg_vec<T, V>(o + g, th);
+  if (o) stg_tile<T, V>(o + g, th, live);
   return nrm;
 }
 
@@ -284,19 +332,21 @@ __device__ __forceinline__ Vec<T, V> hopf_norm(const TileParams& p, const unsign
 // other, so the walk needs no kind switch, no operand selection, and the atan2 can skip the sign
 // logic of the operand that is known to be a norm.
 template <typename T, int V, int CHAIN>
-__global__ void __launch_bounds__(32 + kGroupThreads * max_groups<T>(), 1)
+__global__ void __launch_bounds__(32 + kGroupThreads * max_groups<T, V * (int)sizeof(T) / 16>(), 1)
     from_cartesian_tiled(const __grid_constant__ TileParams p, int64_t n_tiles, int n_groups, int n_bufs, int tail_points) {
   constexpr int P = kGroupThreads * V;
+  constexpr int V0 = 16 / (int)sizeof(T), U = V / V0;
+  constexpr uint32_t kTileRowBytes = (uint32_t)(kRowBytes * U);
   extern __shared__ __align__(128) unsigned char smem_raw[];
   PoolShared* sh = pool_init(smem_raw, n_groups, n_bufs);
   unsigned char* bufs = smem_raw + kPoolHeader;
   const int nn = p.n_nodes;
   const int n_rows = p.n_rows;
-  const uint32_t buf_bytes = (uint32_t)n_rows * (uint32_t)kRowBytes;
+  const uint32_t buf_bytes = (uint32_t)n_rows * kTileRowBytes;
   const int tid = threadIdx.x;
   const int warp = warp_index_uniform();
   if (warp == 0) {
-    producer_loop<T>(p, bufs, buf_bytes, n_groups, n_bufs, n_tiles, tail_points, sh);
+    producer_loop<T, U>(p, bufs, buf_bytes, n_groups, n_bufs, n_tiles, tail_points, sh);
     return;
   }
   const int t = (tid - 32) & (kGroupThreads - 1);
@@ -307,22 +357,22 @@ __global__ void __launch_bounds__(32 + kGroupThreads * max_groups<T>(), 1)
     US_ASSERT(group < n_groups && at.b >= 0 && at.b < n_bufs && at.slot >= 0 && at.slot < kGroupSlots);
     US_ASSERT(kPoolHeader + (size_t)(at.b + 1) * buf_bytes <= (size_t)kSmemBytes);
     mbar_wait(&sh->full[group][at.slot], at.parity);
-    const int64_t g = at.tile * P + (int64_t)t * V;
-    const bool live = tail_points == 0 || at.tile != n_tiles - 1 || t * V < tail_points;  // see to_cartesian_tiled
+    const int64_t g = at.tile * P + (int64_t)t * V0;
+    const uint32_t live = live_chunks<T, V>(t, at.tile, n_tiles, tail_points);
     if (live) {
     if (r_out) {
       // leaves in c_nodes order, sequential, each square and each add rounded once
       Vec<T, V> acc;
       for (int l = 0; l < n_rows; ++l) {
-        const Vec<T, V> x = lds_at<T, V>(mine, (uint32_t)l * kRowBytes);
+        const Vec<T, V> x = lds_at<T, V>(mine, (uint32_t)l * kTileRowBytes);
         sumsq_step<V>(acc.v, x.v, l == 0);
       }
       sqrt_vec<V>(acc.v);
-      stg_vec<T, V>(r_out + g, acc);
+      stg_tile<T, V>(r_out + g, acc, live);
     }
     Vec<T, V> cur;
     if constexpr (CHAIN >= 3) {
-      cur = hopf_norm<T, V, CHAIN - 1, 0>(p, mine, g);
+      cur = hopf_norm<T, V, CHAIN - 1, 0>(p, mine, g, live);
     } else if constexpr (CHAIN != 0) {
       // fast paths unchecked; one range test per point at the end (us_common.cuh: chain_in_range)
       Vec<T, V> in_s, in_c;
@@ -333,7 +383,7 @@ __global__ void __launch_bounds__(32 + kGroupThreads * max_groups<T>(), 1)
         Vec<T, V> th;
         node_from_fast_vec<V>(in_s.v, in_c.v, th.v, cur.v);
         T* o = (T*)d.out_a;
-        if (o) stg_vec<T, V>(o + g, th);
+        if (o) stg_tile<T, V>(o + g, th, live);
       }
 #pragma unroll 2
       for (int k = nn - 2; k >= 0; --k) {
@@ -346,12 +396,12 @@ __global__ void __launch_bounds__(32 + kGroupThreads * max_groups<T>(), 1)
           node_from_fast_vec<V, false, true>(leaf.v, cur.v, th.v, nxt.v);  // theta = atan2(leaf, norm)
         cur = nxt;
         T* o = (T*)d.out_a;
-        if (o) stg_vec<T, V>(o + g, th);
+        if (o) stg_tile<T, V>(o + g, th, live);
       }
       bool ok = true;
 #pragma unroll
       for (int v = 0; v < V; ++v) ok = ok && chain_in_range(in_s.v[v], in_c.v[v], cur.v[v]);
-      if (!ok) chain_redo<T, V, CHAIN>(p, mine, g);
+      if (!ok) chain_redo<T, V, CHAIN>(p, mine, g, live);
     } else {
       // Any tree: one specialised body per node kind (warp-uniform switch), so that no operand has
       // to be selected at run time and the atan2 can drop the sign logic of operands that are norms.
@@ -387,7 +437,7 @@ __global__ void __launch_bounds__(32 + kGroupThreads * max_groups<T>(), 1)
         }
         cur = nxt;
         T* o = (T*)d.out_a;
-        if (o) stg_vec<T, V>(o + g, th);
+        if (o) stg_tile<T, V>(o + g, th, live);
       }
     }
     }
@@ -402,9 +452,9 @@ __global__ void __launch_bounds__(32 + kGroupThreads * max_groups<T>(), 1)
 // =================================================================================================
 static bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
 
-template <typename T>
+template <typename T, int U>
 static const void* variant(bool to, int chain) {
-  constexpr int V = 16 / (int)sizeof(T);
+  constexpr int V = U * 16 / (int)sizeof(T);
   if (to) return (const void*)&to_cartesian_tiled<T, V>;
   if (chain == 1) return (const void*)&from_cartesian_tiled<T, V, 1>;
   if (chain == 2) return (const void*)&from_cartesian_tiled<T, V, 2>;
@@ -497,6 +547,7 @@ struct Tuning {
   int bufs = env_int("US_TILE_BUFS", 0);            // buffers in the pool (0: as many as fit)
   int max_rows = env_int("US_TILE_MAX_ROWS", 13);   // wider trees take the row-ring kernels
   int min_tiles = env_int("US_TILED_MIN_TILES", 8); // per SM: smaller batches take the strided kernels
+  int tile_u = env_int("US_TILE_U", 0);             // 16-byte chunks of a row per tile consumer thread (0: 2 for float64 where it fits, else 1)
   int ring_ctas = env_int("US_RING_CTAS", 0);       // resident CTAs per SM the ring kernels size their slots for (0: automatic)
   int ring_u = env_int("US_RING_U", 0);             // 16-byte chunks of a row per ring consumer thread (0: 2)
   int ring_slots = env_int("US_RING_SLOTS", 0);     // cap on the row slots of a ring (0: as many as fit)
@@ -516,10 +567,10 @@ static Tuning& tuning() {
 // create_hopf(3) float32, whose interpreted walk needs the warps).  So: all the groups the register
 // file holds, and 32 KB worth of buffers beyond them (at least one); the float64 trees are
 // compute-bound and indifferent.  false: the tree is too wide for tiles.
-static bool pool_geometry(int n_rows, int g_max, int* n_groups, int* n_bufs) {
+static bool pool_geometry(int n_rows, int u, int g_max, int* n_groups, int* n_bufs) {
   const Tuning& t = tuning();
   if (n_rows > t.max_rows || n_rows > kTileCap + 1) return false;
-  const int buf = n_rows * kRowBytes;
+  const int buf = n_rows * kRowBytes * u;
   int s_fit = (kSmemBytes - kPoolHeader) / buf;
   if (s_fit > kMaxBuffers) s_fit = kMaxBuffers;
   int extra = 32 * 1024 / buf;
@@ -550,11 +601,24 @@ static int try_tiled(const XformParams& p, int dtype, cudaStream_t st) {
   for (int i = 0; i < n_out; ++i)
     if (p.out[i] && !aligned16(p.out[i])) return kNotTaken;
   if (!TO && p.r_out && !aligned16(p.r_out)) return kNotTaken;
-  int P = kGroupThreads * (16 / esz);
+  // Two chunks per thread: float64 to_cartesian where the pool still holds four groups and a spare
+  // buffer (trees of up to 11 rows at 4 KB a row): +10 % (create_hopf(3), create_standard_prime(8),
+  // create_standard(9): 0.81-0.83 -> 0.91-0.93 of the HBM peak after idle, 0.78 -> 0.84-0.85
+  // sustained).  float64 from_cartesian loses with it (96 registers spill, a third fewer warps:
+  // -7 %) and float32 sits on HBM either way; the tile_u knob (1 / 2) forces the choice for A/B.
+  int u = 1, n_groups = 0, n_bufs = 0;
+  bool fits = false;
+  const bool want_u2 = tuning().tile_u == 2 || (tuning().tile_u == 0 && TO && dtype == US_F64);
+  if (want_u2 && (TO || dtype == US_F64)) {
+    const int g2 = dtype == US_F32 ? max_groups<float, 2>() : max_groups<double, 2>();
+    fits = pool_geometry(n_rows, 2, g2, &n_groups, &n_bufs) && (n_groups >= 4 || tuning().groups > 0);
+    if (fits) u = 2;
+  }
+  if (!fits) fits = pool_geometry(n_rows, 1, dtype == US_F32 ? max_groups<float>() : max_groups<double>(), &n_groups, &n_bufs);
+  int P = kGroupThreads * (16 / esz) * u;
   int64_t n_tiles = p.n / P;
   int64_t done = 0;
-  int n_groups = 0, n_bufs = 0;
-  if (!pool_geometry(n_rows, dtype == US_F32 ? max_groups<float>() : max_groups<double>(), &n_groups, &n_bufs)) {
+  if (!fits) {
     // wide tree: the rows stream through a ring instead of whole tiles being resident
     const int ring_p = ring_points_per_tile(dtype);
     if (p.n / ring_p < 2 * sm_count()) return kNotTaken;
@@ -569,8 +633,10 @@ static int try_tiled(const XformParams& p, int dtype, cudaStream_t st) {
     const int64_t rest = p.n - n_tiles * P;
     const int tail_points = (rest > 0 && (rest * esz) % 16 == 0) ? (int)rest : 0;
     if (tail_points) ++n_tiles;
-    const void* fn = dtype == US_F32 ? variant<float>(TO, chain_kind(p.plan)) : variant<double>(TO, chain_kind(p.plan));
-    const size_t smem = (size_t)kPoolHeader + (size_t)n_bufs * n_rows * kRowBytes;
+    const int shape = chain_kind(p.plan);
+    const void* fn = dtype == US_F32 ? (u == 2 ? (const void*)&to_cartesian_tiled<float, 8> : variant<float, 1>(TO, shape))
+                                     : (u == 2 ? variant<double, 2>(TO, shape) : variant<double, 1>(TO, shape));
+    const size_t smem = (size_t)kPoolHeader + (size_t)n_bufs * n_rows * kRowBytes * u;
     const int threads = 32 + kGroupThreads * n_groups;
     int per_sm = 0;
     if (int rc = resident_ctas(fn, smem, threads, &per_sm)) return rc;
@@ -578,7 +644,7 @@ static int try_tiled(const XformParams& p, int dtype, cudaStream_t st) {
     int64_t grid = sm_count();
     if (grid > n_tiles) grid = n_tiles;
     TileParams body;
-    if (!build_walk<kTileCap>(p, TO, (uint32_t)kRowBytes, 0u, body)) return kNotTaken;
+    if (!build_walk<kTileCap>(p, TO, (uint32_t)(kRowBytes * u), 0u, body)) return kNotTaken;
     int64_t tiles = n_tiles;
     int tail = tail_points;
     void* args[] = {(void*)&body, (void*)&tiles, (void*)&n_groups, (void*)&n_bufs, (void*)&tail};
@@ -611,6 +677,7 @@ int set_tile_tuning(const char* name, int value) {
   else if (!strcmp(name, "tile_bufs")) t.bufs = value;
   else if (!strcmp(name, "tile_max_rows")) t.max_rows = value;
   else if (!strcmp(name, "tiled_min_tiles")) t.min_tiles = value;
+  else if (!strcmp(name, "tile_u")) t.tile_u = (value == 1 || value == 2) ? value : 0;
   else if (!strcmp(name, "ring_ctas")) t.ring_ctas = value < 0 ? 0 : (value > 4 ? 4 : value);
   else if (!strcmp(name, "ring_u")) t.ring_u = (value == 1 || value == 2) ? value : 0;
   else if (!strcmp(name, "ring_slots")) t.ring_slots = value < 0 ? 0 : value;

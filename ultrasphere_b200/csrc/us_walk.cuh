@@ -46,6 +46,8 @@ struct WalkParams {
   int32_t n_rows;           // rows staged per tile
   int32_t has_r;            // to: the last row is r
   int32_t max_park;         // parking rows needed (plan.max_stack); 0: no `c` node
+  int32_t zero;             // always 0, but only the host knows: lets a kernel tie an instruction to a loaded register (ring kernels)
+  int32_t reserved[3];
 };
 
 // Fill the descriptors from the plan and the pointer tables of an XformParams.  `row_scale` turns a
@@ -62,6 +64,8 @@ inline bool build_walk(const XformParams& p, bool to, uint32_t row_scale, uint32
   w.has_r = (to && p.r_in) ? 1 : 0;
   w.r_out = to ? nullptr : p.r_out;
   w.max_park = p.plan.max_stack;
+  w.zero = 0;
+  w.reserved[0] = w.reserved[1] = w.reserved[2] = 0;
   const int n_in = to ? nn : p.plan.n_leaves;
   for (int i = 0; i < n_in; ++i) w.in[i] = p.in[i];
   if (w.has_r) w.in[nn] = p.r_in;
