@@ -5,7 +5,7 @@
 // has 33 rows).  Here the rows stream through a RING of row slots instead: the producer warp
 // issues one TMA bulk copy per (tile, row) in exactly the order the consumers will need them, each
 // slot has its own full/empty mbarrier pair, and a consumer warp releases a slot as soon as it has
-// used the row.  Shared memory per CTA is (slots + parking rows) * slot size whatever the tree width.
+// used the row (RingConsumer::release: not before its loads from the slot have returned).  Shared memory per CTA is (slots + parking rows) * slot size whatever the tree width.
 // A thread owns U 16-byte chunks of every row (U * 16 B / sizeof(T) points; chunk u of a slot holds
 // the 256 threads' u-th chunks back to back, so shared-memory loads stay conflict-free and every
 // global store instruction of a warp covers 512 contiguous bytes): the per-row handshake, the

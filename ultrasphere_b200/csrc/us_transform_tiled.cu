@@ -1,7 +1,8 @@
 // Cartesian <-> polyspherical transforms: contiguous fast path.
 //
 // One persistent CTA per SM: one producer warp + G consumer GROUPS of four warps.  A tile is 128*V
-// points (V = 16 bytes / sizeof(T)); each input array contributes one 2 KB row of it.  The tiles
+// points (V = U * 16 bytes / sizeof(T); U = 1, or 2 for float64 to_cartesian); each input array
+// contributes one row of U * 2 KB.  The tiles
 // of a CTA travel through a pool of S > G shared-memory buffers: the producer brings tile i into
 // buffer i mod S with one TMA bulk copy per row (cp.async.bulk, completing on a "full" mbarrier),
 // group i mod G works on it, and each of the group's warps arrives on the buffer's "empty"
@@ -9,18 +10,18 @@
 // may have outstanding (its j-th tile uses barrier j mod 8): successive uses of one buffer go to
 // different groups, and a parity wait on a barrier shared between groups can be satisfied by the
 // wrong phase once the groups drift two uses apart (seen as stale tiles and hangs on the HBM-bound
-// float32 trees); a barrier only one group waits on, in order, cannot alias.  So G tiles are being computed on while S - G
-// tiles are in flight or landed — memory-level parallelism comes from the copy engine and is sized
-// by the shared memory left over, not by registers — and no warp ever waits for a warp of another
-// group.  The pool is cut to the tree: S = what fits in 227 KB, G = as many groups as the register
-// file holds (7 for float32, 6 for float64), fewer for wide trees.
+// float32 trees); a barrier only one group waits on, in order, cannot alias.  So G tiles are being
+// computed on while S - G tiles are in flight or landed, and no warp ever waits for a warp of another
+// group.  The pool is cut to the tree (pool_geometry below): G = as many groups as the register file
+// holds (7 for float32, 6 for float64, 4-5 with U = 2), S = G + 32 KB worth of buffers — NOT all of
+// shared memory: more tiles in flight than the latency-bandwidth product needs slow DRAM down.
 // (The first version ran 2-3 CTAs of 8 consumer warps with two stages each: trees of 9+ rows fit
 // only two such CTAs, i.e. 4 warps per scheduler for kernels that are latency-bound, and ncu showed
 // 9 % of the warp samples sitting in the full-barrier wait.)
 //
-// Every consumer thread owns V consecutive points: one 128-bit LDS per input row, the node
-// descriptors of us_walk.cuh (kernel-parameter constant bank, warp-uniform control flow), one
-// 128-bit streaming STG per output row.  Deferred branches of `c` nodes are parked in dead rows of
+// Every consumer thread owns U runs of 16 bytes of every row: one 128-bit LDS per input row and
+// chunk, the node descriptors of us_walk.cuh (kernel-parameter constant bank, warp-uniform control
+// flow), one 128-bit streaming STG per output row and chunk.  Deferred branches of `c` nodes are parked in dead rows of
 // the tile (us_walk.cuh): no per-thread stack, no local memory.
 //
 // HBM traffic = algorithmic traffic: every input element is read once, every output written once
