@@ -181,6 +181,20 @@ def test_no_slot_is_released_before_its_loads_return():
     done = subprocess.run([sys.executable, os.path.join(root, "tools", "sass_release_scan.py")], capture_output=True, text=True, timeout=600)
     assert done.returncode == 0, done.stdout[-3000:]
     assert "release-before-use: 0 of" in done.stdout and "from_cartesian_ring" in done.stdout and "wreduce_tma" in done.stdout
+    # the checker itself: the pattern the ring kernels shipped with before the fix is flagged, the fixed one is not
+    sys.path.insert(0, os.path.join(root, "tools"))
+    try:
+        from sass_release_scan import scan
+    finally:
+        sys.path.pop(0)
+    head = "\tFunction : k\n"
+    load = "        /*0010*/                   LDS.128 R16, [R10] ;\n        /*0020*/                   LDS.128 R20, [R10+0x1000] ;\n"
+    arrive = "        /*0050*/              @!P1 SYNCS.ARRIVE.TRANS64.A1T0 RZ, [R11+URZ+0x100], RZ ;\n"
+    use = "        /*0030*/                   LOP3.LUT R2, R16, R20, RZ, 0xfc, !PT ;\n"
+    unrelated = "        /*0030*/                   IADD3 R2, PT, PT, R3, 0x1, RZ ;\n"
+    assert scan(head + load + unrelated + arrive)[:2] == (2, 2)
+    assert scan(head + load + use + arrive)[:2] == (0, 2)
+    assert scan(head + load + "        /*0030*/                   MEMBAR.SC.CTA ;\n" + arrive)[:2] == (0, 2)
 
 
 def test_rule_backend_switch_and_rule_parameters():
