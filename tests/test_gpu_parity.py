@@ -707,6 +707,8 @@ def test_ring_geometry_does_not_change_the_bits(spec, tdt):
     ("random:32:0", torch.float32, 64_000_000, {b"ring_slots": 4, b"ring_ctas": 3}),
     ("random:32:0", torch.float64, 32_000_000, {}),
     ("standard:9", torch.float32, 256_000_000, {}),
+    ("hopf:3", torch.float64, 128_000_000, {}),
+    ("standard_prime:8", torch.float64, 128_000_000, {b"tile_u": 2}),
 ])
 def test_back_to_back_launches_are_deterministic(spec, tdt, n, knobs):
     """from_cartesian and to_cartesian launched back to back, over and over, at the BASELINE sizes:
