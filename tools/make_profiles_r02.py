@@ -104,7 +104,7 @@ if os.path.isfile(lp):
             tot[r[ki]] = tot.get(r[ki], 0) + ms(r)
             cnt[r[ki]] += 1
     all_ms = sum(tot.values())
-    L = [f"# {R} — ncu launch list of `python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-quadrature --no-configs`", "",
+    L = [f"# {R} — ncu launch list of `python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-quadrature --no-configs --no-sustained`", "",
          "`ncu --metrics gpu__time_duration.sum --clock-control none -c 80` (cold-cache, serialised: compare SHARES).", "",
          "| kernel | launches | total ms | share |", "|---|---|---|---|"]
     for k, v in sorted(tot.items(), key=lambda kv: -kv[1]):
